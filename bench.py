@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- cell-updates/s of the full time step (incl. the Poisson solve) + HBM-roofline fraction.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl b200|reference]
+
+A "step" is one TimeIntegrator::step over the whole synthetic grid.  ONE JSON line goes to stdout.
+
+  value        whole-job cell-updates/s, State resident in HBM, K steps enqueued back to back, device-timed
+  e2e          the same metric through the C ABI with HOST buffers: every step uploads u, v, p from pinned host memory,
+               runs the step and downloads u, v, p, rhs (what a GUI-style caller of TimeIntegrator::step(State&) sees)
+  roofline     the dominant stage of the step: algorithmic bytes / live CUDA-event time, against the
+               measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline the reference's own OpenMP solver (oracle/_ref, else the C port) on this box's host cores, bounded sample
+
+Workloads are BASELINE.json's configs on synthetic (deterministic preset) data; the default is the one its metric and
+target are quoted on: jet plume, --solver=mg --vcycles=2, 8192^2 fp64 per GPU (weak scaling over row slabs).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# name -> (preset, solver, nx, ny_per_gpu, Lx, Ly_per_gpu, vcycles, tol, pcg_max_iters, BASELINE config index)
+WORKLOADS = {
+    "jet_mg_8192": ("jet", "mg", 8192, 8192, 1.0, 1.0, 2, 1e-6, 200, 4),
+    "jet_pcg_8192": ("jet", "pcg", 8192, 8192, 1.0, 1.0, 2, 1e-6, 200, 4),
+    "lid_mg_8192": ("lid", "mg", 8192, 8192, 1.0, 1.0, 2, 1e-6, 200, 3),
+    "shear_pcg_4096": ("shear", "pcg", 4096, 4096, 1.0, 1.0, 2, 1e-6, 200, 2),
+    "jet_mg_1024": ("jet", "mg", 1024, 1024, 1.0, 1.0, 2, 1e-6, 200, 1),
+    "lid_pcg_512x256": ("lid", "pcg", 512, 256, 2.0, 1.0, 2, 1e-8, 200, 0),
+}
+DEFAULT_WORKLOAD = "jet_mg_8192"
+
+# Algorithmic HBM bytes per cell of each stage (fp64; SURVEY.md §8d, restated in DESIGN.md).
+STAGE_BYTES = {"cfl_dt": 16, "rhs_stage1": 32, "rhs_stage2": 48, "divergence": 24, "project": 40, "divergence_post": 24}
+
+
+def solve_bytes(solver, vcycles, iters):
+    """mg: 64 B/cell per smooth() call; PCG: 32 (init) + 64 per iteration as implemented (Ap recomputed, z never
+    stored; SURVEY's store-Ap formulation would be 80)."""
+    return 64 * vcycles if solver == "mg" else 32 + 64 * iters
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc, self.index = None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        out = self.proc.communicate()[0]
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_run(wl, steps, warmup, sample_n):
+    """The reference's OpenMP solver on the host cores, on a bounded sample (a sample_n^2 grid of the same preset
+    and solver settings; cell-updates/s is size-independent once the fields leave the CPU caches)."""
+    ncores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(ncores)
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    from oracle import cfdo
+    kind = "ref" if cfdo.have_ref() else "port"
+    lib = cfdo.load(kind)
+    preset, solver, _, _, Lx, Ly, vcycles, tol, iters, _ = wl
+    nx = ny = sample_n
+    bc, Re, CFL = cfdo.preset(preset, Ly)
+    pp = cfdo.make_params(solver, vcycles=vcycles, tol=tol, pcg_max_iters=iters)
+    sim = cfdo.Sim(lib, nx, ny, Lx, Ly)
+    if preset == "shear":
+        cfdo.shear_init(sim.u, nx, ny, Ly)
+    for _ in range(warmup):
+        sim.step(bc, Re, CFL, pp)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sim.step(bc, Re, CFL, pp)
+    dt = time.perf_counter() - t0
+    sim.close()
+    return {"value": nx * ny * steps / dt, "unit": "cell-updates/s", "cores": ncores,
+            "kind": "reference" if kind == "ref" else "port",
+            "sample": f"{preset} {solver} {nx}x{ny}, {steps} steps after {warmup} warm-up, OMP_NUM_THREADS={ncores}",
+            "seconds": dt}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--variant", type=int, default=1)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    wl = WORKLOADS[args.workload]
+    preset, solver, nx, ny_gpu, Lx, Ly_gpu, vcycles, tol, iters, cfg_idx = wl
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    N = args.gpus
+    ny, Ly = ny_gpu * N, Ly_gpu * N  # weak scaling: row slabs stacked in y
+    config = {"workload": args.workload, "baseline_config": cfg_idx, "preset": preset, "solver": solver,
+              "grid": f"{nx}x{ny}", "domain": f"{Lx}x{Ly}", "vcycles": vcycles, "tol": tol, "pcg_max_iters": iters,
+              "decomposition": f"{N} row slab(s) of {nx}x{ny_gpu}",
+              "l2": "fields (>= 0.5 GB each) exceed the 126 MB L2" if nx * ny_gpu * 8 > 200e6 else
+              "L2 flushed (256 MB write) before every timed step"}
+    base = {"metric": "cell-updates/s (full timestep incl. Poisson)", "unit": "cell-updates/s", "n_gpus": N,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic (deterministic preset initial/boundary data)",
+            "config": config}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample_n = 2048 if solver == "mg" else 768
+        r = cpu_reference_run(wl, args.steps, args.warmup, sample_n)
+        line = dict(base, impl="reference", value=r["value"], ms_per_step=1e3 * r["seconds"] / args.steps,
+                    cpu_baseline={k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                    e2e={"value": r["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    gpu_launches=0)
+        print(json.dumps(line))
+        return
+
+    import torch
+    if world != N:
+        raise SystemExit(f"--gpus {N} needs {N} ranks (torchrun --nproc-per-node {N}); WORLD_SIZE={world}")
+    if N > 1:
+        raise SystemExit("row-slab multi-GPU path not available in this build")
+    torch.cuda.set_device(local_rank)
+    cfd = importlib.import_module("macos-cfd_b200")
+    bc, Re, CFL = cfd.preset(preset, Ly)
+    pp = cfd.make_params(solver, vcycles=vcycles, tol=tol, pcg_max_iters=iters)
+    s = cfd.Solver(nx, ny, Lx, Ly, device=local_rank)
+    s.set_variant(args.variant)
+    sh = s.shapes()
+    if preset == "shear":
+        s.upload(u=cfd.shear_initial_u(nx, ny, Ly))
+    stream = torch.cuda.ExternalStream(s.stream, device=local_rank)
+    flush = None if nx * ny_gpu * 8 > 200e6 else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    cells = nx * ny
+
+    for _ in range(args.warmup):
+        s.step_async(bc, Re, CFL, pp)
+    s.sync()
+
+    # ---- device-resident timing: K steps, CUDA events on the launching stream
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = s.launch_count
+    torch.cuda.synchronize()
+    if flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            s.step_async(bc, Re, CFL, pp)
+        e1.record(stream)
+        info = s.sync()
+        torch.cuda.synchronize()
+        total_ms = e0.elapsed_time(e1)
+    else:
+        total_ms = 0.0
+        for _ in range(args.steps):
+            with torch.cuda.stream(stream):
+                flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            s.step_async(bc, Re, CFL, pp)
+            e1.record(stream)
+            info = s.sync()
+            total_ms += e0.elapsed_time(e1)
+    launches = s.launch_count - l0
+    clocks = sampler.stop()
+    ms_per_step = total_ms / args.steps
+    value = cells * args.steps / (total_ms * 1e-3)
+
+    # ---- per-stage CUDA-event times of a step (live, same run) -> roofline of the dominant stage
+    s.set_profiling(True)
+    acc = {}
+    nprof = max(3, min(args.steps, 5))
+    for _ in range(nprof):
+        if flush is not None:
+            with torch.cuda.stream(stream):
+                flush.fill_(1)
+        s.step(bc, Re, CFL, pp)
+        for k, v in s.stage_times().items():
+            acc[k] = acc.get(k, 0.0) + v / nprof
+    s.set_profiling(False)
+    peak, peak_src = measured_peaks()
+    stage_bytes = dict(STAGE_BYTES, pressure_solve=solve_bytes(solver, vcycles, info.iters))
+    stages = {}
+    for k, ms in acc.items():
+        b = stage_bytes.get(k, 0) * cells
+        stages[k] = {"ms": round(ms, 4), "gbs": round(b / (ms * 1e-3) / 1e9, 1) if ms > 0 and b else None}
+    top = max((k for k in acc if stage_bytes.get(k)), key=lambda k: acc[k])
+    achieved = stage_bytes[top] * cells / (acc[top] * 1e-3) / 1e9
+    step_bytes = sum(stage_bytes.values()) * cells
+    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_cell": stage_bytes[top],
+                "whole_step": {"bytes_per_cell": sum(stage_bytes.values()),
+                               "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                               "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
+                "stages": stages}
+
+    # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        hu = torch.zeros(sh["u"], dtype=torch.float64).pin_memory()
+        hv = torch.zeros(sh["v"], dtype=torch.float64).pin_memory()
+        hp = torch.zeros(sh["p"], dtype=torch.float64).pin_memory()
+        hr = torch.zeros(sh["p"], dtype=torch.float64).pin_memory()
+        s.download(hu, hv, hp, hr)
+        ke = max(2, min(args.steps, 4))
+        for _ in range(1):
+            s.upload(hu, hv, hp); s.step(bc, Re, CFL, pp); s.download(hu, hv, hp, hr)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            s.upload(hu, hv, hp)
+            s.step(bc, Re, CFL, pp)
+            s.download(hu, hv, hp, hr)
+        torch.cuda.synchronize()
+        t = time.perf_counter() - t0
+        h2d = (hu.numel() + hv.numel() + hp.numel()) * 8
+        d2h = h2d + hr.numel() * 8
+        e2e = {"value": cells * ke / t, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": ke, "ms_per_step": 1e3 * t / ke,
+               "path": "cfd_b200_upload -> cfd_b200_step -> cfd_b200_download (pinned host State)"}
+        del hu, hv, hp, hr
+
+    line = dict(base, value=value, ms_per_step=ms_per_step, clocks=clocks, e2e=e2e, gpu_launches=launches,
+                roofline=roofline, last_step={"dt": info.dt, "residual": info.residual, "iters": info.iters})
+    s.close()
+    if not args.no_cpu_baseline:
+        r = cpu_reference_run(wl, 2, 1, 4096 if solver == "mg" else 1024)
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,579 @@
+// capi.cu -- implementation of include/cfd_b200.h: device State, launch sequences, host<->device copies.
+// The launch sequence of one step follows TimeIntegrator::step (time_integrator.cpp:47-239) line by line; see
+// enqueue_step().  No CPU fallback exists: every entry point needs a CUDA device.
+#include "../../include/cfd_b200.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+#include "kernels_pressure.cuh"
+#include "kernels_step.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                                \
+    do {                                                                                                        \
+        cudaError_t e_ = (call);                                                                                \
+        if (e_ != cudaSuccess)                                                                                  \
+            return fail(e_ == cudaErrorMemoryAllocation ? CFD_B200_ENOMEM : CFD_B200_ECUDA, "%s:%d %s: %s",     \
+                        __FILE__, __LINE__, #call, cudaGetErrorString(e_));                                     \
+    } while (0)
+
+enum { ST_BC0 = 0, ST_CFL, ST_RHS1, ST_BC1, ST_RHS2, ST_BC2, ST_DIV, ST_SOLVE, ST_PROJECT, ST_BC3, ST_DIV2, ST_END, ST_COUNT };
+const char *const kStageNames[ST_COUNT - 1] = {"bc_pre", "cfl_dt", "rhs_stage1", "bc_stage1", "rhs_stage2", "bc_stage2",
+                                               "divergence", "pressure_solve", "project", "bc_post", "divergence_post"};
+
+} // namespace
+
+struct cfd_b200_solver {
+    Geom g{};
+    int device = 0;
+    int rank = 0, nranks = 1;
+    size_t n = 0; // doubles per field
+    double *u = nullptr, *v = nullptr, *p = nullptr, *rhs = nullptr;
+    double *u1 = nullptr, *v1 = nullptr;           // TimeIntegrator work arrays (time_integrator.hpp:18-19)
+    double *r = nullptr, *sA = nullptr, *sB = nullptr; // PressureSolver work arrays (pressure.hpp:29); z, Ap never stored
+    double *scratch_u = nullptr, *scratch_v = nullptr; // stage-level entry points only (lazy)
+    Scalars *d_sc = nullptr;
+    Scalars *h_sc = nullptr; // pinned
+    double *partials = nullptr;
+    size_t partials_n = 0;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    int variant = 1;
+    int profiling = 0;
+    cudaEvent_t ev[ST_COUNT] = {};
+    bool ev_valid = false;
+    int sm_count = 148;
+};
+
+namespace {
+
+#define LAUNCH(s, kernel, grid, block, ...)                                                                     \
+    do {                                                                                                        \
+        kernel<<<grid, block, 0, (s)->stream>>>(__VA_ARGS__);                                                   \
+        (s)->launches++;                                                                                        \
+    } while (0)
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+int alloc_field(cfd_b200_solver *s, double **ptr) {
+    CU(cudaMalloc(ptr, s->n * sizeof(double)));
+    CU(cudaMemsetAsync(*ptr, 0, s->n * sizeof(double), s->stream));
+    return 0;
+}
+
+void fill_geom(Geom &g, int nx, int ny_glob, double Lx, double Ly, int j0, int ny_loc, int bottom, int top) {
+    g.nx = nx;
+    g.ny = ny_loc;
+    g.ny_glob = ny_glob;
+    g.j0 = j0;
+    g.bottom = bottom;
+    g.top = top;
+    g.P = ((nx + 3 + CFD_XOFF + 2) + 15) / 16 * 16;
+    g.rows = ny_loc + 3 + 2 * CFD_YOFF;
+    // Grid::init, grid.cpp:10-11 -- the same expressions on the host, so every constant is the reference's double
+    g.dx = Lx / static_cast<double>(nx);
+    g.dy = Ly / static_cast<double>(ny_glob);
+    g.idx = 1.0 / g.dx;
+    g.idy = 1.0 / g.dy;
+    g.idx2 = 1.0 / (g.dx * g.dx);
+    g.idy2 = 1.0 / (g.dy * g.dy);
+    g.denom = 2.0 * (g.idx2 + g.idy2);
+    g.inv_denom = 1.0 / g.denom;
+    int e = 0;
+    g.denom_pow2 = (std::frexp(g.denom, &e) == 0.5) ? 1 : 0;
+    double diag = 2.0 * (g.idx2 + g.idy2);
+    g.inv_diag = 1.0 / (diag < 1e-12 ? 1e-12 : diag); // 1.0 / std::max(diag, 1e-12), pressure.cpp:163
+}
+
+BcD to_bcd(const cfd_b200_bc *b) {
+    BcD d;
+    auto side = [](const cfd_b200_bc_side &s) { return BcSideD{s.type, s.moving, s.inflow_u, s.inflow_v}; };
+    d.left = side(b->left);
+    d.right = side(b->right);
+    d.bottom = side(b->bottom);
+    d.top = side(b->top);
+    d.jet_center = b->jet_center;
+    d.jet_width = b->jet_width;
+    return d;
+}
+
+void stage_mark(cfd_b200_solver *s, int st) {
+    if (s->profiling) cudaEventRecord(s->ev[st], s->stream);
+}
+
+// apply_bc_u / apply_bc_v / apply_bc_p in the reference's pass order (left/right, then bottom/top)
+void enqueue_bc(cfd_b200_solver *s, const BcD &bc, double *u, double *v, double *p, int sanitize) {
+    const Geom &g = s->g;
+    LAUNCH(s, k_bc_lr, cdiv(g.ny + 1, 128), 128, g, bc, u, v, p, sanitize, s->d_sc);
+    if (g.bottom || g.top) LAUNCH(s, k_bc_bt, cdiv(g.nx + 3, 128), 128, g, bc, u, v, p, sanitize, s->d_sc);
+}
+
+void enqueue_cfl(cfd_b200_solver *s, double Re, double CFL, double dt_override, int cfl_only) {
+    const Geom &g = s->g;
+    dim3 grid(cdiv(g.P / 2, 256), g.ny + 1 < 64 ? g.ny + 1 : 64);
+    LAUNCH(s, k_absmax, grid, 256, g, s->u, s->v, s->d_sc);
+    // (slabs: max-allreduce of umax/vmax goes here)
+    LAUNCH(s, k_dt, 1, 1, g, Re, CFL, dt_override, s->d_sc, cfl_only);
+}
+
+template <int MODE>
+void enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, const double *vin, double *uout, double *vout) {
+    const Geom &g = s->g;
+    RhsConst k{g.idx, g.idy, g.idx2, g.idy2, invRe};
+    dim3 grid(cdiv(g.nx + 1, RHS_TX), cdiv(g.ny + 1, RHS_TY)), block(RHS_TX, RHS_TY);
+    LAUNCH(s, k_rhs_simple<MODE>, grid, block, g, k, uin, vin, uout, vout, s->d_sc);
+}
+
+dim3 row_grid(const cfd_b200_solver *s, int ncols, int nrows, int *rows_per_block) {
+    // <= ~4096 blocks: one x-block per 256 columns, contiguous row chunks in y
+    int gx = cdiv(ncols, 256);
+    int gy_max = 4096 / gx;
+    if (gy_max < 1) gy_max = 1;
+    int rpb = cdiv(nrows, gy_max);
+    if (rpb < 4) rpb = 4;
+    *rows_per_block = rpb;
+    return dim3(gx, cdiv(nrows, rpb));
+}
+
+void enqueue_divergence(cfd_b200_solver *s, int pre, int want_sum) {
+    const Geom &g = s->g;
+    int rpb = 4;
+    dim3 grid = row_grid(s, g.nx, g.ny, &rpb);
+    if (pre)
+        LAUNCH(s, k_divergence<1>, grid, 256, g, s->u, s->v, s->rhs, s->p, s->d_sc, s->partials, want_sum, rpb);
+    else
+        LAUNCH(s, k_divergence<0>, grid, 256, g, s->u, s->v, s->rhs, (double *)nullptr, s->d_sc, s->partials, want_sum, rpb);
+}
+
+int pcg_grid(const cfd_b200_solver *s, int ntiles) {
+    int cap = s->sm_count * 4;
+    return ntiles < cap ? ntiles : cap;
+}
+
+// PressureSolver::solve, pressure.cpp:113-242.  The whole solve is enqueued; convergence is tested on the device.
+int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
+    const Geom &g = s->g;
+    if (pp->solver == CFD_B200_SOLVER_PCG) {
+        cudaMemsetAsync(s->p, 0, s->n * sizeof(double), s->stream); // pressure.cpp:133-134
+        {
+            dim3 grid(cdiv(g.nx, 512), g.ny < 256 ? g.ny : 256);
+            LAUNCH(s, k_pcg_init, grid, PT_THREADS, g, s->rhs, s->r, s->d_sc, s->partials, pp->tol, pp->pcg_max_iters, 1);
+        }
+        const int ntx = cdiv(g.nx, PT_X), nty = cdiv(g.ny, PT_Y), ntiles = ntx * nty;
+        const int grid = pcg_grid(s, ntiles);
+        double *s_old = s->sA, *s_new = s->sB;
+        for (int it = 0; it < pp->pcg_max_iters; ++it) {
+            LAUNCH(s, k_pcg_phase1, grid, PT_THREADS, g, s->r, s_old, s_new, s->d_sc, s->partials, ntx, ntiles, 1);
+            LAUNCH(s, k_pcg_phase2, grid, PT_THREADS, g, s->p, s->r, s_new, s->d_sc, s->partials, ntx, ntiles, pp->tol,
+                   pp->pcg_max_iters, 1);
+            double *t = s_old;
+            s_old = s_new;
+            s_new = t;
+        }
+    } else {
+        if (pp->mg_mode != CFD_B200_MG_REFERENCE)
+            return fail(CFD_B200_EUNSUPPORTED, "mg_mode=VCYCLE is not implemented yet");
+        LAUNCH(s, k_solve_begin, 1, 1, s->d_sc);
+        dim3 cblock(32, 8), cgrid(cdiv(cdiv(g.nx, 2), 32), cdiv(g.ny, 8));
+        dim3 rgrid(cdiv(g.nx, 256), g.ny < 256 ? g.ny : 256);
+        for (int vc = 0; vc < pp->vcycles; ++vc) {
+            for (int sweep = 0; sweep < 2; ++sweep) // the literal 2 of pressure.cpp:119
+                for (int colour = 0; colour < 2; ++colour) {
+                    if (g.denom_pow2)
+                        LAUNCH(s, k_rbgs_colour<1>, cgrid, cblock, g, s->p, s->rhs, colour, s->d_sc);
+                    else
+                        LAUNCH(s, k_rbgs_colour<0>, cgrid, cblock, g, s->p, s->rhs, colour, s->d_sc);
+                }
+            LAUNCH(s, k_rbgs_residual, rgrid, 256, g, s->p, s->rhs, s->d_sc, s->partials, pp->tol, 1);
+        }
+    }
+    LAUNCH(s, k_solve_finish, 1, 1, s->d_sc);
+    return 0;
+}
+
+void enqueue_project(cfd_b200_solver *s, const Scalars *dt_src, double dt_arg) {
+    const Geom &g = s->g;
+    int rpb = 4;
+    dim3 grid = row_grid(s, g.nx + 1, g.ny + 1, &rpb);
+    LAUNCH(s, k_project, grid, 256, g, s->u, s->v, s->p, dt_src, dt_arg, s->d_sc, rpb);
+}
+
+// TimeIntegrator::step, time_integrator.cpp:47-239
+int enqueue_step(cfd_b200_solver *s, const cfd_b200_bc *bc_in, double Re, double CFL, const cfd_b200_params *pp,
+                 double dt_override) {
+    const Geom &g = s->g;
+    const BcD bc = to_bcd(bc_in);
+    const bool both_bt = bc.bottom.type == BC_PERIODIC && bc.top.type == BC_PERIODIC;
+    if (both_bt && s->nranks > 1)
+        return fail(CFD_B200_EUNSUPPORTED, "bottom/top Periodic is not supported across row slabs");
+    const double invRe = 1.0 / Re; // "1.0 / Re" at time_integrator.cpp:76
+    stage_mark(s, ST_BC0);
+    enqueue_bc(s, bc, s->u, s->v, s->p, 0); // :51-53
+    stage_mark(s, ST_CFL);
+    enqueue_cfl(s, Re, CFL, dt_override, 0); // :55-66
+    stage_mark(s, ST_RHS1);
+    enqueue_rhs<1>(s, invRe, s->u, s->v, s->u1, s->v1); // :71-103
+    stage_mark(s, ST_BC1);
+    enqueue_bc(s, bc, s->u1, s->v1, nullptr, 1); // :106-107
+    stage_mark(s, ST_RHS2);
+    enqueue_rhs<2>(s, invRe, s->u1, s->v1, s->u, s->v); // :109-147
+    stage_mark(s, ST_BC2);
+    enqueue_bc(s, bc, s->u, s->v, nullptr, 1); // :150-155
+    stage_mark(s, ST_DIV);
+    enqueue_divergence(s, 1, 1); // :158-186
+    stage_mark(s, ST_SOLVE);
+    int rc = enqueue_solve(s, pp); // :187
+    if (rc) return rc;
+    stage_mark(s, ST_PROJECT);
+    enqueue_project(s, s->d_sc, 0.0); // :188-202
+    stage_mark(s, ST_BC3);
+    enqueue_bc(s, bc, s->u, s->v, s->p, 1); // :205-207
+    stage_mark(s, ST_DIV2);
+    enqueue_divergence(s, 0, 1); // :210-220
+    LAUNCH(s, k_sanitize_if, s->sm_count * 4, 256, g, s->p, s->d_sc); // :236
+    stage_mark(s, ST_END);
+    s->ev_valid = s->profiling != 0;
+    CU(cudaMemcpyAsync(s->h_sc, s->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+void fill_info(const cfd_b200_solver *s, cfd_b200_step_info *info) {
+    if (!info) return;
+    const Scalars &h = *s->h_sc;
+    info->dt = h.dt;
+    info->residual = h.res;
+    info->iters = h.iters;
+    info->pcg_breakdown = h.breakdown_iter;
+    info->div_before = h.div_before;
+    info->div_after = h.div_after;
+    info->nonfinite = (h.nonfinite_any ? 1 : 0) | (h.nonfinite_res ? 2 : 0);
+}
+
+// host (reference layout) <-> device (padded layout) copy of one field
+int copy_field(cfd_b200_solver *s, double *dev, double *host, int host_pitch, int host_rows, bool to_device) {
+    const Geom &g = s->g;
+    double *d0 = dev + gidx(g, 0, 0);
+    if (to_device)
+        CU(cudaMemcpy2DAsync(d0, (size_t)g.P * 8, host, (size_t)host_pitch * 8, (size_t)host_pitch * 8, host_rows,
+                             cudaMemcpyHostToDevice, s->stream));
+    else
+        CU(cudaMemcpy2DAsync(host, (size_t)host_pitch * 8, d0, (size_t)g.P * 8, (size_t)host_pitch * 8, host_rows,
+                             cudaMemcpyDeviceToHost, s->stream));
+    return 0;
+}
+
+int need_scratch(cfd_b200_solver *s) {
+    if (!s->scratch_u) {
+        int rc = alloc_field(s, &s->scratch_u);
+        if (rc) return rc;
+        rc = alloc_field(s, &s->scratch_v);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int cfd_b200_abi_version(void) { return CFD_B200_ABI_VERSION; }
+const char *cfd_b200_last_error(void) { return g_err; }
+
+int cfd_b200_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(CFD_B200_ENODEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+int cfd_b200_comm_id(void *) { return fail(CFD_B200_EUNSUPPORTED, "multi-GPU slabs are not built into this library yet"); }
+
+int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int rank, int nranks, const void *,
+                         cfd_b200_solver **out) {
+    if (!out) return fail(CFD_B200_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (nx < 4 || ny < 4 || !(Lx > 0.0) || !(Ly > 0.0)) return fail(CFD_B200_EINVAL, "need nx, ny >= 4 and Lx, Ly > 0");
+    if (nranks != 1 || rank != 0) return fail(CFD_B200_EUNSUPPORTED, "multi-GPU slabs are not built into this library yet");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(CFD_B200_ENODEVICE, "no CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return fail(CFD_B200_EINVAL, "device %d out of range [0,%d)", device, ndev);
+    CU(cudaSetDevice(device));
+    cfd_b200_solver *s = new (std::nothrow) cfd_b200_solver;
+    if (!s) return fail(CFD_B200_ENOMEM, "host allocation failed");
+    s->device = device;
+    s->rank = rank;
+    s->nranks = nranks;
+    fill_geom(s->g, nx, ny, Lx, Ly, 0, ny, 1, 1);
+    s->n = (size_t)s->g.P * s->g.rows;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->sm_count = prop.multiProcessorCount;
+    int rc = 0;
+    do {
+        if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(CFD_B200_ECUDA, "stream create failed"); break; }
+        double **fields[] = {&s->u, &s->v, &s->p, &s->rhs, &s->u1, &s->v1, &s->r, &s->sA, &s->sB};
+        for (double **f : fields)
+            if ((rc = alloc_field(s, f)) != 0) break;
+        if (rc) break;
+        if (cudaMalloc(&s->d_sc, sizeof(Scalars)) != cudaSuccess) { rc = fail(CFD_B200_ENOMEM, "scalars alloc failed"); break; }
+        cudaMemsetAsync(s->d_sc, 0, sizeof(Scalars), s->stream);
+        if (cudaMallocHost(&s->h_sc, sizeof(Scalars)) != cudaSuccess) { rc = fail(CFD_B200_ENOMEM, "pinned alloc failed"); break; }
+        memset(s->h_sc, 0, sizeof(Scalars));
+        s->partials_n = 2 * 65536;
+        if (cudaMalloc(&s->partials, s->partials_n * sizeof(double)) != cudaSuccess) { rc = fail(CFD_B200_ENOMEM, "partials alloc failed"); break; }
+        for (int i = 0; i < ST_COUNT; ++i)
+            if (cudaEventCreate(&s->ev[i]) != cudaSuccess) { rc = fail(CFD_B200_ECUDA, "event create failed"); break; }
+        if (rc) break;
+        if (cudaStreamSynchronize(s->stream) != cudaSuccess) { rc = fail(CFD_B200_ECUDA, "init sync failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    } while (0);
+    if (rc) {
+        cfd_b200_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return 0;
+}
+
+int cfd_b200_create(int nx, int ny, double Lx, double Ly, int device, cfd_b200_solver **out) {
+    return cfd_b200_create_slab(nx, ny, Lx, Ly, device, 0, 1, nullptr, out);
+}
+
+int cfd_b200_slab_rows(const cfd_b200_solver *s, int *row0, int *nrows) {
+    if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
+    if (row0) *row0 = s->g.j0;
+    if (nrows) *nrows = s->g.ny;
+    return 0;
+}
+
+void cfd_b200_destroy(cfd_b200_solver *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    double *fields[] = {s->u, s->v, s->p, s->rhs, s->u1, s->v1, s->r, s->sA, s->sB, s->scratch_u, s->scratch_v, s->partials};
+    for (double *f : fields)
+        if (f) cudaFree(f);
+    if (s->d_sc) cudaFree(s->d_sc);
+    if (s->h_sc) cudaFreeHost(s->h_sc);
+    for (int i = 0; i < ST_COUNT; ++i)
+        if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int cfd_b200_upload(cfd_b200_solver *s, const double *u, const double *v, const double *p) {
+    if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
+    CU(cudaSetDevice(s->device));
+    const Geom &g = s->g;
+    int rc = 0;
+    if (u && (rc = copy_field(s, s->u, const_cast<double *>(u), g.nx + 3, g.ny + 2, true))) return rc;
+    if (v && (rc = copy_field(s, s->v, const_cast<double *>(v), g.nx + 2, g.ny + 3, true))) return rc;
+    if (p && (rc = copy_field(s, s->p, const_cast<double *>(p), g.nx + 2, g.ny + 2, true))) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int cfd_b200_upload_rhs(cfd_b200_solver *s, const double *rhs) {
+    if (!s || !rhs) return fail(CFD_B200_EINVAL, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    int rc = copy_field(s, s->rhs, const_cast<double *>(rhs), s->g.nx + 2, s->g.ny + 2, true);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int cfd_b200_download(cfd_b200_solver *s, double *u, double *v, double *p, double *rhs) {
+    if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
+    CU(cudaSetDevice(s->device));
+    const Geom &g = s->g;
+    int rc = 0;
+    if (u && (rc = copy_field(s, s->u, u, g.nx + 3, g.ny + 2, false))) return rc;
+    if (v && (rc = copy_field(s, s->v, v, g.nx + 2, g.ny + 3, false))) return rc;
+    if (p && (rc = copy_field(s, s->p, p, g.nx + 2, g.ny + 2, false))) return rc;
+    if (rhs && (rc = copy_field(s, s->rhs, rhs, g.nx + 2, g.ny + 2, false))) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int cfd_b200_download_work(cfd_b200_solver *s, double *u1, double *v1) {
+    if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
+    CU(cudaSetDevice(s->device));
+    const Geom &g = s->g;
+    int rc = 0;
+    if (u1 && (rc = copy_field(s, s->u1, u1, g.nx + 3, g.ny + 2, false))) return rc;
+    if (v1 && (rc = copy_field(s, s->v1, v1, g.nx + 2, g.ny + 3, false))) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int cfd_b200_clear_work(cfd_b200_solver *s) {
+    if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemsetAsync(s->u1, 0, s->n * sizeof(double), s->stream));
+    CU(cudaMemsetAsync(s->v1, 0, s->n * sizeof(double), s->stream));
+    return 0;
+}
+
+int cfd_b200_step_async(cfd_b200_solver *s, const cfd_b200_bc *bc, double Re, double CFL, const cfd_b200_params *pp,
+                        double dt_override) {
+    if (!s || !bc || !pp) return fail(CFD_B200_EINVAL, "NULL argument");
+    if (pp->solver != CFD_B200_SOLVER_PCG && pp->solver != CFD_B200_SOLVER_MG) return fail(CFD_B200_EINVAL, "bad solver type");
+    CU(cudaSetDevice(s->device));
+    return enqueue_step(s, bc, Re, CFL, pp, dt_override);
+}
+
+int cfd_b200_sync(cfd_b200_solver *s, cfd_b200_step_info *info) {
+    if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    fill_info(s, info);
+    return 0;
+}
+
+int cfd_b200_step(cfd_b200_solver *s, const cfd_b200_bc *bc, double Re, double CFL, const cfd_b200_params *pp,
+                  double dt_override, cfd_b200_step_info *info) {
+    int rc = cfd_b200_step_async(s, bc, Re, CFL, pp, dt_override);
+    if (rc) return rc;
+    return cfd_b200_sync(s, info);
+}
+
+int cfd_b200_divergence_l2(cfd_b200_solver *s, double *out) {
+    if (!s || !out) return fail(CFD_B200_EINVAL, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    const Geom &g = s->g;
+    CU(cudaMemsetAsync(&s->d_sc->diag_max_bits, 0, sizeof(unsigned long long), s->stream));
+    dim3 grid(cdiv(g.nx, 256), g.ny < 128 ? g.ny : 128);
+    LAUNCH(s, k_diag, grid, 256, g, s->u, s->v, s->d_sc, s->partials);
+    CU(cudaMemcpyAsync(s->h_sc, s->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    double denom = static_cast<double>(g.nx) * g.ny_glob; // metrics.cpp:84
+    *out = std::sqrt(s->h_sc->diag_sum / denom);
+    return 0;
+}
+
+int cfd_b200_max_velocity(cfd_b200_solver *s, double *out) {
+    double dummy;
+    int rc = cfd_b200_divergence_l2(s, &dummy);
+    if (rc) return rc;
+    if (!out) return fail(CFD_B200_EINVAL, "NULL argument");
+    unsigned long long b = s->h_sc->diag_max_bits;
+    memcpy(out, &b, sizeof(double));
+    return 0;
+}
+
+int cfd_b200_apply_bc(cfd_b200_solver *s, const cfd_b200_bc *bc, int which) {
+    if (!s || !bc) return fail(CFD_B200_EINVAL, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    enqueue_bc(s, to_bcd(bc), (which & 1) ? s->u : nullptr, (which & 2) ? s->v : nullptr, (which & 4) ? s->p : nullptr, 0);
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int cfd_b200_compute_cfl(cfd_b200_solver *s, double Re, double CFL, double *dt_out) {
+    if (!s || !dt_out) return fail(CFD_B200_EINVAL, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    enqueue_cfl(s, Re, CFL, 0.0, 1);
+    CU(cudaMemcpyAsync(s->h_sc, s->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    *dt_out = s->h_sc->dt;
+    return 0;
+}
+
+int cfd_b200_rhs_terms(cfd_b200_solver *s, double invRe, double *du, double *dv) {
+    if (!s || !du || !dv) return fail(CFD_B200_EINVAL, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    int rc = need_scratch(s);
+    if (rc) return rc;
+    const Geom &g = s->g;
+    CU(cudaMemsetAsync(s->scratch_u, 0, s->n * sizeof(double), s->stream)); // advect_* zero-fill first (advection.cpp:41)
+    CU(cudaMemsetAsync(s->scratch_v, 0, s->n * sizeof(double), s->stream));
+    enqueue_rhs<0>(s, invRe, s->u, s->v, s->scratch_u, s->scratch_v);
+    if ((rc = copy_field(s, s->scratch_u, du, g.nx + 3, g.ny + 2, false))) return rc;
+    if ((rc = copy_field(s, s->scratch_v, dv, g.nx + 2, g.ny + 3, false))) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int cfd_b200_divergence(cfd_b200_solver *s) {
+    if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
+    CU(cudaSetDevice(s->device));
+    enqueue_divergence(s, 0, 0);
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int cfd_b200_pressure_solve(cfd_b200_solver *s, const cfd_b200_params *pp, double *residual, int *iters) {
+    if (!s || !pp) return fail(CFD_B200_EINVAL, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    int rc = enqueue_solve(s, pp);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(s->h_sc, s->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    if (residual) *residual = s->h_sc->res;
+    if (iters) *iters = s->h_sc->iters;
+    return 0;
+}
+
+int cfd_b200_subtract_grad_p(cfd_b200_solver *s, double dt) {
+    if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
+    CU(cudaSetDevice(s->device));
+    enqueue_project(s, nullptr, dt);
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+long long cfd_b200_launch_count(const cfd_b200_solver *s) { return s ? s->launches : 0; }
+
+int cfd_b200_set_profiling(cfd_b200_solver *s, int on) {
+    if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
+    s->profiling = on ? 1 : 0;
+    s->ev_valid = false;
+    return 0;
+}
+
+int cfd_b200_stage_times(cfd_b200_solver *s, int n, const char **names, float *ms) {
+    if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
+    if (!s->ev_valid) return fail(CFD_B200_EINVAL, "no profiled step: call cfd_b200_set_profiling(s,1) and run a step");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    int count = ST_COUNT - 1;
+    for (int i = 0; i < count && i < n; ++i) {
+        if (names) names[i] = kStageNames[i];
+        if (ms) CU(cudaEventElapsedTime(&ms[i], s->ev[i], s->ev[i + 1]));
+    }
+    return count;
+}
+
+void *cfd_b200_stream(cfd_b200_solver *s) { return s ? (void *)s->stream : nullptr; }
+
+int cfd_b200_set_variant(cfd_b200_solver *s, int variant) {
+    if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
+    s->variant = variant;
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,432 @@
+// kernels_step.cuh -- boundary conditions, CFL/dt, the fused advection+diffusion+RK kernels, divergence and
+// pressure-gradient projection.  Every arithmetic expression keeps the reference's operand order; the
+// comment on each device function names the reference lines it restates.
+#pragma once
+#include "common.cuh"
+
+// =========================================================================================================
+// Boundary conditions  (bc.cpp:31-380).  The reference applies each field's BC in two ordered passes:
+// left/right over rows, then bottom/top over columns (which therefore owns the corner faces), with the
+// Outflow copies of the second pass reading values the first pass wrote.  Two launches keep that order:
+// k_bc_lr (one thread per row: u, v and p of that row) and k_bc_bt (one thread per column).
+// `sanitize` additionally applies sanitize_field (time_integrator.cpp:8-27) to the ghost cells, which no
+// producing kernel writes (interior values are sanitised where they are produced).
+// =========================================================================================================
+
+// bc.cpp:7-29
+__device__ __forceinline__ double jet_profile(const BcD &bc, double y) {
+    double mask = (fabs(y - bc.jet_center) <= 0.5 * bc.jet_width) ? 1.0 : 0.0;
+    return bc.left.inflow_u * mask;
+}
+
+// One side of one line: Wall -> 0, Moving -> mov, Inflow -> inf, Outflow -> copy of `inner`, Periodic -> nothing.
+__device__ __forceinline__ bool side_value(int type, double mov, double inf, double inner, double &val) {
+    switch (type) {
+    case BC_WALL: val = 0.0; return true;
+    case BC_MOVING: val = mov; return true;
+    case BC_INFLOW: val = inf; return true;
+    case BC_OUTFLOW: val = inner; return true;
+    default: return false;
+    }
+}
+
+// left/right pass on one row; row points at raw column 0; the right boundary line is raw column cR.
+__device__ __forceinline__ void bc_row(double *row, int cR, bool both, int ltype, double lmov, double linf,
+                                       int rtype, double rmov, double rinf, bool sanitize, int &flag) {
+    if (sanitize) {
+        row[0] = sanitize_val(row[0], flag);
+        row[cR + 1] = sanitize_val(row[cR + 1], flag);
+    }
+    double val;
+    if (!both && side_value(ltype, lmov, linf, row[2], val)) {
+        row[1] = val;
+        row[0] = val;
+    }
+    if (side_value(rtype, rmov, rinf, row[cR - 1], val)) {
+        row[cR] = val;
+        row[cR + 1] = val;
+    }
+    if (both) { // bc.cpp:95-107 / :252-264 -- the boundary columns swap on every call
+        double lb = row[1], li = row[2], rb = row[cR], ri = row[cR - 1];
+        row[0] = ri;
+        row[1] = rb;
+        row[cR] = lb;
+        row[cR + 1] = li;
+    }
+}
+
+__global__ void k_bc_lr(Geom g, BcD bc, double *u, double *v, double *p, int sanitize, Scalars *sc) {
+    int jj = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    int flag = 0;
+    bool both = bc.left.type == BC_PERIODIC && bc.right.type == BC_PERIODIC;
+    if (u && jj <= g.ny) { // apply_bc_u rows, bc.cpp:38-107: u is the normal component here
+        double y = ((g.j0 + jj - 1) + 0.5) * g.dy;
+        bc_row(u + gidx(g, 0, jj), g.nx + 1, both, bc.left.type, 0.0, jet_profile(bc, y), bc.right.type, 0.0,
+               bc.right.inflow_u, sanitize, flag);
+    }
+    if (v && jj <= v_rows(g)) { // apply_bc_v rows, bc.cpp:192-264: tangential; left Inflow gives 0
+        bc_row(v + gidx(g, 0, jj), g.nx, both, bc.left.type, bc.left.moving, 0.0, bc.right.type,
+               bc.right.moving, bc.right.inflow_v, sanitize, flag);
+    }
+    if (p && jj <= g.ny) { // apply_bc_p rows, bc.cpp:340-358
+        double *row = p + gidx(g, 0, jj);
+        if (sanitize) {
+            row[0] = sanitize_val(row[0], flag);
+            row[g.nx + 1] = sanitize_val(row[g.nx + 1], flag);
+        }
+        double first = row[1], last = row[g.nx];
+        row[0] = both ? last : first;
+        row[g.nx + 1] = both ? first : last;
+    }
+    if (flag) sc->nonfinite_any = 1;
+}
+
+// bottom/top pass on one column; col points at raw row 0 of that column; rT = top boundary line.
+__device__ __forceinline__ void bc_col(double *col, size_t P, int rT, bool both, bool do_b, bool do_t, int btype,
+                                       double bmov, double binf, int ttype, double tmov, double tinf) {
+    double val;
+    if (do_b && side_value(btype, bmov, binf, col[2 * P], val)) {
+        col[P] = val;
+        col[0] = val;
+    }
+    if (do_t && side_value(ttype, tmov, tinf, col[(size_t)(rT - 1) * P], val)) {
+        col[(size_t)rT * P] = val;
+        col[(size_t)(rT + 1) * P] = val;
+    }
+    if (both) { // bc.cpp:171-183 / :318-330 (single-slab handles only; rejected on the host otherwise)
+        double bb = col[P], bi = col[2 * P], tb = col[(size_t)rT * P], ti = col[(size_t)(rT - 1) * P];
+        col[0] = ti;
+        col[P] = tb;
+        col[(size_t)rT * P] = bb;
+        col[(size_t)(rT + 1) * P] = bi;
+    }
+}
+
+__global__ void k_bc_bt(Geom g, BcD bc, double *u, double *v, double *p, int sanitize, Scalars *sc) {
+    int ii = blockIdx.x * blockDim.x + threadIdx.x; // raw column 0 .. nx+2
+    int flag = 0;
+    bool both = bc.bottom.type == BC_PERIODIC && bc.top.type == BC_PERIODIC;
+    const size_t P = g.P;
+    if (u && ii <= g.nx + 2) {
+        double *col = u + gidx(g, ii, 0);
+        if (sanitize) { // ghost rows (true domain ghosts only)
+            if (g.bottom) col[0] = sanitize_val(col[0], flag);
+            if (g.top) col[(size_t)(g.ny + 1) * P] = sanitize_val(col[(size_t)(g.ny + 1) * P], flag);
+        }
+        if (ii >= 1 && ii <= g.nx + 1) // apply_bc_u columns, bc.cpp:111-183: tangential
+            bc_col(col, P, g.ny, both, g.bottom, g.top, bc.bottom.type, bc.bottom.moving, bc.bottom.inflow_u,
+                   bc.top.type, bc.top.moving, bc.top.inflow_u);
+    }
+    if (v && ii <= g.nx + 1) {
+        double *col = v + gidx(g, ii, 0);
+        if (sanitize) {
+            if (g.bottom) col[0] = sanitize_val(col[0], flag);
+            if (g.top) col[(size_t)(g.ny + 2) * P] = sanitize_val(col[(size_t)(g.ny + 2) * P], flag);
+        }
+        if (ii >= 1 && ii <= g.nx) // apply_bc_v columns, bc.cpp:268-330: normal (Wall and Moving give 0)
+            bc_col(col, P, g.ny + 1, both, g.bottom, g.top, bc.bottom.type, 0.0, bc.bottom.inflow_v, bc.top.type,
+                   0.0, bc.top.inflow_v);
+    }
+    if (p && ii <= g.nx + 1) {
+        double *col = p + gidx(g, ii, 0);
+        if (sanitize) {
+            if (g.bottom) col[0] = sanitize_val(col[0], flag);
+            if (g.top) col[(size_t)(g.ny + 1) * P] = sanitize_val(col[(size_t)(g.ny + 1) * P], flag);
+        }
+        if (ii >= 1 && ii <= g.nx) { // apply_bc_p columns, bc.cpp:361-379
+            double first = col[P], last = col[(size_t)g.ny * P];
+            if (g.bottom) col[0] = both ? last : first;
+            if (g.top) col[(size_t)(g.ny + 1) * P] = both ? first : last;
+        }
+    }
+    if (flag) sc->nonfinite_any = 1;
+}
+
+// =========================================================================================================
+// compute_cfl (metrics.cpp:6-50) + the dt logic of TimeIntegrator::step (time_integrator.cpp:55-66)
+// =========================================================================================================
+
+// max |q| over the faces ii in [1,IX], jj in [1,JY]; block = 256 threads = 512 columns as double2
+__global__ void k_absmax(Geom g, const double *__restrict__ u, const double *__restrict__ v, Scalars *sc) {
+    const int c2 = blockIdx.x * blockDim.x + threadIdx.x; // double2 index along the pitch
+    const int ii = 2 * c2 - CFD_XOFF;                     // raw column of .x; .y is ii+1
+    double mu = 0.0, mv = 0.0;
+    if (2 * c2 + 1 < g.P) {
+        const int JYv = v_rows(g);
+        for (int jj = 1 + blockIdx.y; jj <= JYv; jj += gridDim.y) {
+            const size_t off = (size_t)(jj + CFD_YOFF) * g.P + 2 * c2;
+            if (jj <= g.ny) {
+                double2 a = *reinterpret_cast<const double2 *>(u + off);
+                if (ii >= 1 && ii <= g.nx + 1) mu = max2(mu, fabs(a.x));
+                if (ii + 1 >= 1 && ii + 1 <= g.nx + 1) mu = max2(mu, fabs(a.y));
+            }
+            double2 b = *reinterpret_cast<const double2 *>(v + off);
+            if (ii >= 1 && ii <= g.nx) mv = max2(mv, fabs(b.x));
+            if (ii + 1 >= 1 && ii + 1 <= g.nx) mv = max2(mv, fabs(b.y));
+        }
+    }
+    block_max_to_global(mu, &sc->umax_bits);
+    block_max_to_global(mv, &sc->vmax_bits);
+}
+
+// One thread: dt from umax/vmax exactly as the host code does, and reset of the per-step accumulators.
+__global__ void k_dt(Geom g, double Re, double CFL, double dt_override, Scalars *sc, int cfl_only) {
+    double umax = __longlong_as_double((long long)sc->umax_bits);
+    double vmax = __longlong_as_double((long long)sc->vmax_bits);
+    sc->umax_bits = 0ull;
+    sc->vmax_bits = 0ull;
+    // metrics.cpp:26-49
+    double dt_diff = 0.5 * Re * min2(g.dx * g.dx, g.dy * g.dy);
+    double dt_adv = 1e30;
+    if (umax > 1e-12 && umax < 1e6) dt_adv = min2(dt_adv, g.dx / umax);
+    if (vmax > 1e-12 && vmax < 1e6) dt_adv = min2(dt_adv, g.dy / vmax);
+    if (dt_adv >= 1e30) dt_adv = dt_diff;
+    double dt_min = 1e-6;
+    double dt = max2(min2(dt_adv, dt_diff), dt_min);
+    dt = CFL * dt;
+    dt = clamp3(dt, dt_min, 1e-3);
+    if (!cfl_only) { // time_integrator.cpp:55-66
+        double dt_cfl = dt;
+        if (dt_override > 0.0) dt = min2(dt_cfl, dt_override);
+        double dt_cap = (dt_override > 0.0) ? dt_override : 1e-3;
+        if (!finite_d(dt) || dt <= 0.0) dt = min2(1e-3, dt_diff);
+        dt = clamp3(dt, 1e-8, dt_cap);
+    }
+    sc->dt = dt;
+    sc->inv_dt = 1.0 / dt; // time_integrator.cpp:179 "(1.0 / dt)"
+    sc->div_before = 0.0;
+    sc->div_after = 0.0;
+    sc->nonfinite_any = 0;
+    sc->nonfinite_p = 0;
+    sc->nonfinite_res = 0;
+    sc->breakdown_iter = -1;
+    sc->iters = 0;
+}
+
+// =========================================================================================================
+// Advection + diffusion + Runge-Kutta update, fused (advection.cpp:33-421, diffusion.cpp:5-39,
+// time_integrator.cpp:71-143).  du_dt / dv_dt are never materialised in the step.
+// =========================================================================================================
+
+// advection.cpp:10-12
+__device__ __forceinline__ double minmod(double a, double b) {
+    return (a * b <= 0.0) ? 0.0 : (fabs(a) < fabs(b) ? a : b);
+}
+// MUSCL/minmod face flux between samples c and p1 of the stencil (m1, c, p1, p2), carried by w:
+// advection.cpp:59-69 for the "+" face, :72-81 for the "-" face (same expression one sample to the left),
+// clip_face_states = :15-31.
+__device__ __forceinline__ double muscl_flux(double m1, double c, double p1, double p2, double w) {
+    double sc = minmod(c - m1, p1 - c);
+    double sp = minmod(p1 - c, p2 - p1);
+    double qL = c + 0.5 * sc;
+    double qR = p1 - 0.5 * sp;
+    double lo = min2(m1, min2(c, p1));
+    double hi = max2(m1, max2(c, p1));
+    qL = clamp3(qL, lo, hi);
+    qR = clamp3(qR, lo, hi);
+    return (w > 0.0 ? qL : qR) * w;
+}
+// first-order upwind flux of the outer ring, e.g. advection.cpp:133
+__device__ __forceinline__ double upwind1(double a, double b, double w) { return (w > 0.0 ? a : b) * w; }
+
+struct RhsConst {
+    double idx, idy, idx2, idy2, invRe;
+};
+
+// d(q)/dt at one face.  qc/uc/vc point at (ii,jj) of the q/u/v tiles (row stride S).  In raw indices both
+// advect_u and advect_v carry q with x-face velocities u(ii,jj), u(ii-1,jj) and y-face velocities v(ii,jj),
+// v(ii,jj-1) (advection.cpp:68,80,101,113 and :263,275,296,308).  ex/ey = -1/0/+1 mark the first-order ring
+// (advection.cpp:124-225, :319-419); corner faces stay 0 and get no diffusion (diffusion.cpp:12-13).
+__device__ __forceinline__ double rhs_point(const double *qc, const double *uc, const double *vc, int S, int ex,
+                                            int ey, const RhsConst &k) {
+    if (ex != 0 && ey != 0) return 0.0;
+    const double c = qc[0];
+    const double wxp = uc[0], wxm = uc[-1], wyp = vc[0], wym = vc[-S];
+    double d;
+    if (ex == 0 && ey == 0) {
+        double fxp = muscl_flux(qc[-1], c, qc[1], qc[2], wxp);
+        double fxm = muscl_flux(qc[-2], qc[-1], c, qc[1], wxm);
+        double fyp = muscl_flux(qc[-S], c, qc[S], qc[2 * S], wyp);
+        double fym = muscl_flux(qc[-2 * S], qc[-S], c, qc[S], wym);
+        double conv = (fxp - fxm) * k.idx + (fyp - fym) * k.idy;
+        double lap = (qc[1] - 2.0 * c + qc[-1]) * k.idx2 + (qc[S] - 2.0 * c + qc[-S]) * k.idy2;
+        d = -conv;
+        d = d + k.invRe * lap; // du_dt += invRe * lap
+    } else {
+        double fxp = (ex == 1) ? 0.0 : upwind1(c, qc[1], wxp);
+        double fxm = (ex == -1) ? 0.0 : upwind1(qc[-1], c, wxm);
+        double fyp = (ey == 1) ? 0.0 : upwind1(c, qc[S], wyp);
+        double fym = (ey == -1) ? 0.0 : upwind1(qc[-S], c, wym);
+        double conv = (fxp - fxm) * k.idx + (fyp - fym) * k.idy;
+        d = -conv;
+    }
+    return d;
+}
+
+// MODE 0: write the sanitised derivatives (stage-level parity entry point cfd_b200_rhs_terms)
+// MODE 1: RK stage 1   out = sanitize(in + dt * sanitize(d))                 (time_integrator.cpp:81-103)
+// MODE 2: RK stage 2   acc = sanitize(0.5 * (acc + in + dt * sanitize(d)))   (time_integrator.cpp:119-147)
+//         (in = u1/v1 is the field the derivative is taken of; acc = s.u/s.v, updated in place)
+#define RHS_TX 32
+#define RHS_TY 8
+template <int MODE>
+__global__ void __launch_bounds__(RHS_TX *RHS_TY)
+    k_rhs_simple(Geom g, RhsConst k, const double *__restrict__ uin, const double *__restrict__ vin, double *uout,
+                 double *vout, Scalars *sc) {
+    constexpr int S = RHS_TX + 4 + 1; // +1: odd stride
+    __shared__ double us[(RHS_TY + 4) * S], vs[(RHS_TY + 4) * S];
+    const int x0 = 1 + blockIdx.x * RHS_TX, y0 = 1 + blockIdx.y * RHS_TY;
+    const int tid = threadIdx.y * RHS_TX + threadIdx.x;
+    const int max_col = g.P - CFD_XOFF - 1, max_row = g.rows - CFD_YOFF - 1;
+    for (int t = tid; t < (RHS_TY + 4) * (RHS_TX + 4); t += RHS_TX * RHS_TY) {
+        int ly = t / (RHS_TX + 4), lx = t - ly * (RHS_TX + 4);
+        int ii = x0 - 2 + lx, jj = y0 - 2 + ly;
+        double a = 0.0, b = 0.0;
+        if (ii <= max_col && jj <= max_row) {
+            size_t o = gidx(g, ii, jj);
+            a = uin[o];
+            b = vin[o];
+        }
+        us[ly * S + lx] = a;
+        vs[ly * S + lx] = b;
+    }
+    __syncthreads();
+    const int ii = x0 + threadIdx.x, jj = y0 + threadIdx.y;
+    const int c = (threadIdx.y + 2) * S + threadIdx.x + 2;
+    const double dt = (MODE == 0) ? 0.0 : sc->dt;
+    int flag = 0;
+    const int JYv = v_rows(g);
+    if (ii <= g.nx + 1 && jj <= g.ny) { // u faces: ii in [1, nx+1], jj in [1, ny]
+        int ex = (ii == 1) ? -1 : (ii == g.nx + 1) ? 1 : 0;
+        int ey = (g.bottom && jj == 1) ? -1 : (g.top && jj == g.ny) ? 1 : 0;
+        double d = sanitize_val(rhs_point(us + c, us + c, vs + c, S, ex, ey, k), flag);
+        size_t o = gidx(g, ii, jj);
+        if (MODE == 0) uout[o] = d;
+        if (MODE == 1) uout[o] = sanitize_val(us[c] + dt * d, flag);
+        if (MODE == 2) uout[o] = sanitize_val(0.5 * (uout[o] + us[c] + dt * d), flag);
+    }
+    if (ii <= g.nx && jj <= JYv) { // v faces: ii in [1, nx], jj in [1, ny+1]
+        int ex = (ii == 1) ? -1 : (ii == g.nx) ? 1 : 0;
+        int ey = (g.bottom && jj == 1) ? -1 : (g.top && jj == g.ny + 1) ? 1 : 0;
+        double d = sanitize_val(rhs_point(vs + c, us + c, vs + c, S, ex, ey, k), flag);
+        size_t o = gidx(g, ii, jj);
+        if (MODE == 0) vout[o] = d;
+        if (MODE == 1) vout[o] = sanitize_val(vs[c] + dt * d, flag);
+        if (MODE == 2) vout[o] = sanitize_val(0.5 * (vout[o] + vs[c] + dt * d), flag);
+    }
+    if (flag) sc->nonfinite_any = 1;
+}
+
+// =========================================================================================================
+// divergence (project.cpp:7-42), fused with the serial sum-of-squares loop of TimeIntegrator::step
+// (time_integrator.cpp:162-171 / :211-220) and -- PRE only -- the 1/dt scaling (:174-182) and the p(0,0) pin
+// (:186).  POST leaves the unscaled divergence in rhs (:210), which callers can observe.
+// =========================================================================================================
+template <int PRE>
+__global__ void __launch_bounds__(256)
+    k_divergence(Geom g, const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ rhs,
+                 double *p, Scalars *sc, double *partials, int want_sum, int rpb) {
+    const int ii = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[1] = {0.0};
+    if (ii <= g.nx) {
+        const int jbase = 1 + blockIdx.y * rpb; // contiguous chunk of rpb rows per block
+        const double inv_dt = PRE ? sc->inv_dt : 1.0;
+#pragma unroll 4
+        for (int r = 0; r < rpb; ++r) {
+            const int jj = jbase + r;
+            if (jj > g.ny) break;
+            const size_t o = gidx(g, ii, jj);
+            double uR = fin0(u[o + 1]), uL = fin0(u[o]);
+            double vT = fin0(v[o + g.P]), vB = fin0(v[o]);
+            double divx = (uR - uL) * g.idx;
+            double divy = (vT - vB) * g.idy;
+            double d = fin0(divx + divy);
+            acc[0] += d * d;
+            if (PRE) d = fin0(d * inv_dt);
+            rhs[o] = d;
+        }
+    }
+    if (PRE && p && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && g.j0 == 0)
+        p[gidx(g, 1, 1)] = 0.0; // s.p(0,0) = 0 before the solve, time_integrator.cpp:186
+    if (want_sum) {
+        const double ncell = (double)(g.nx * g.ny_glob); // "(g.nx * g.ny)" is an int product in the reference
+        grid_sum<1>(acc, partials, &sc->ticket[0], [=](double(&t)[1]) {
+            // single-GPU: finish here; slabs finish after the allreduce (host side)
+            if (PRE) sc->div_before = (g.ny == g.ny_glob) ? sqrt(t[0] / ncell) : t[0];
+            else sc->div_after = (g.ny == g.ny_glob) ? sqrt(t[0] / ncell) : t[0];
+        });
+    }
+}
+
+// =========================================================================================================
+// subtract_grad_p (project.cpp:44-84) with the two pins of time_integrator.cpp:186-188 folded in: p(0,0) is
+// read as 0 and written as 0 here.  The inflow re-imposition of :194-202 is exactly what the apply_bc_u call
+// that follows writes for a left Inflow side (bc.cpp:53-57), so it needs no kernel of its own.  Outputs are
+// sanitised here, equivalent to the final sanitize_field calls (:234-235) because the BC pass in between only
+// copies or overwrites values.
+// =========================================================================================================
+__global__ void __launch_bounds__(256)
+    k_project(Geom g, double *__restrict__ u, double *__restrict__ v, double *p, const Scalars *sc, double dt_arg,
+              Scalars *flags, int rpb) {
+    const int ii = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (ii > g.nx + 1) return;
+    const double dt = sc ? sc->dt : dt_arg;
+    const int jbase = 1 + blockIdx.y * rpb;
+    const int JYv = v_rows(g);
+    const bool pin_here = (g.j0 == 0);
+    int flag = 0;
+#pragma unroll 4
+    for (int r = 0; r < rpb; ++r) {
+        const int jj = jbase + r;
+        if (jj > JYv) break;
+        const size_t o = gidx(g, ii, jj);
+        double pc = p[o], pl = p[o - 1], pb = p[o - g.P];
+        if (pin_here) {
+            if (jj == 1 && ii == 1) pc = 0.0;
+            if (jj == 1 && ii == 2) pl = 0.0;
+            if (jj == 2 && ii == 1) pb = 0.0;
+        }
+        if (jj <= g.ny) {
+            double gradp = fin0((pc - pl) * g.idx);
+            u[o] = sanitize_val(u[o] - dt * gradp, flag);
+        }
+        if (ii <= g.nx) {
+            double gradp = fin0((pc - pb) * g.idy);
+            v[o] = sanitize_val(v[o] - dt * gradp, flag);
+        }
+        if (pin_here && jj == 1 && ii == 1) p[o] = 0.0;
+    }
+    if (flag) flags->nonfinite_any = 1;
+}
+
+// sanitize_field(s.p) (time_integrator.cpp:236); only does work when the solver flagged a non-finite p
+__global__ void k_sanitize_if(Geom g, double *a, Scalars *sc) {
+    if (!sc->nonfinite_p) return;
+    size_t n = (size_t)g.P * g.rows;
+    int flag = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        a[i] = sanitize_val(a[i], flag);
+    if (flag) sc->nonfinite_any = 1;
+}
+
+// =========================================================================================================
+// Driver diagnostics: divergence_l2 (metrics.cpp:68-86) and max_velocity (metrics.cpp:52-66)
+// =========================================================================================================
+__global__ void __launch_bounds__(256)
+    k_diag(Geom g, const double *__restrict__ u, const double *__restrict__ v, Scalars *sc, double *partials) {
+    const int ii = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[1] = {0.0};
+    double m = 0.0;
+    if (ii <= g.nx) {
+        for (int jj = 1 + blockIdx.y; jj <= g.ny; jj += gridDim.y) {
+            const size_t o = gidx(g, ii, jj);
+            double ul = u[o], ur = u[o + 1], vb = v[o], vt = v[o + g.P];
+            double d = (ur - ul) * g.idx + (vt - vb) * g.idy; // divx*idx + divy*idy
+            acc[0] += d * d;
+            double uc = 0.5 * (ul + ur), vc = 0.5 * (vb + vt);
+            m = max2(m, sqrt(uc * uc + vc * vc));
+        }
+    }
+    block_max_to_global(m, &sc->diag_max_bits);
+    grid_sum<1>(acc, partials, &sc->ticket[1], [=](double(&t)[1]) { sc->diag_sum = t[0]; });
+}
