@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "kernels_pressure.cuh"
 #include "kernels_step.cuh"
+#include "kernels_rhs_march.cuh"
 
 namespace {
 
@@ -136,8 +137,30 @@ template <int MODE>
 void enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, const double *vin, double *uout, double *vout) {
     const Geom &g = s->g;
     RhsConst k{g.idx, g.idy, g.idx2, g.idy2, invRe};
-    dim3 grid(cdiv(g.nx + 1, RHS_TX), cdiv(g.ny + 1, RHS_TY)), block(RHS_TX, RHS_TY);
-    LAUNCH(s, k_rhs_simple<MODE>, grid, block, g, k, uin, vin, uout, vout, s->d_sc);
+    const dim3 block(RHS_TX, RHS_TY);
+    const int ntx = cdiv(g.nx + 1, RHS_TX), nty = cdiv(g.ny + 1, RHS_TY);
+    auto simple = [&](int tx0, int ty0, int ntx_, int nty_) {
+        if (ntx_ > 0 && nty_ > 0)
+            LAUNCH(s, k_rhs_simple<MODE>, dim3(ntx_, nty_), block, g, k, uin, vin, uout, vout, s->d_sc, tx0, ty0);
+    };
+    // Interior faces (all four fluxes MUSCL, for u and v alike): 2 <= ii <= nx-1, 2 <= jj <= ny-1.  The marching kernel
+    // takes the part of it that is aligned to the simple kernel's tiles; the tile strips around it (ring included)
+    // stay with the simple kernel.  A slab that does not touch the bottom / top has no ring there.
+    const int txr = (g.nx - 1) / RHS_TX;                        // first tile column of the right strip
+    const int tyb = g.bottom ? 1 : 0;                           // tile rows of the bottom strip
+    const int tyt = g.top ? (g.ny - 1) / RHS_TY : nty;          // first tile row of the top strip
+    const int XA = RHS_TX + 1, XB = txr * RHS_TX, YA = tyb * RHS_TY + 1, YB = g.top ? tyt * RHS_TY : g.ny;
+    if (s->variant == 0 || XB < XA + 16 || YB < YA + 8) {
+        simple(0, 0, ntx, nty);
+        return;
+    }
+    const int RY = 64;
+    dim3 mgrid(cdiv(cdiv(XB - XA + 1, MARCH_COLS), MARCH_WARPS), cdiv(YB - YA + 1, RY));
+    LAUNCH(s, k_rhs_march<MODE>, mgrid, 32 * MARCH_WARPS, g, k, uin, vin, uout, vout, s->d_sc, XA, XB, YA, YB, RY);
+    simple(0, 0, ntx, tyb);                    // bottom strip
+    simple(0, tyt, ntx, nty - tyt);            // top strip
+    simple(0, tyb, 1, tyt - tyb);              // left strip
+    simple(txr, tyb, ntx - txr, tyt - tyb);    // right strip
 }
 
 dim3 row_grid(const cfd_b200_solver *s, int ncols, int nrows, int *rows_per_block) {

@@ -1,0 +1,177 @@
+// kernels_rhs_march.cuh -- the optimised advection + diffusion + Runge-Kutta kernel for INTERIOR faces.
+//
+// ncu on the simple tile kernel (profiles/r01_v1_*): issue-bound (76 % issue slots, 624 thread-instructions per
+// cell, 17 % DRAM): every face flux was computed twice (as "+" flux of one face and "-" flux of its neighbour;
+// the two expressions in advection.cpp:59-69 / :72-81 are textually the same function of the same samples), every
+// slope twice more, and clip_face_states' 3-way min/max + two clamps cost 13 FP64 compares and 18 32-bit selects
+// per flux.  This kernel
+//   * marches each thread up a column: the y-stencil (q[j-1..j+2], the slope and the flux of the face below) lives
+//     in registers, so each y-flux and y-slope is computed exactly once;
+//   * gives each thread 2 adjacent columns (one aligned double2 per row and field) and exchanges the x-neighbours'
+//     value / slope / flux with 4 warp shuffles per field: each x-flux and x-slope is computed once per warp
+//     (lanes 0 and 31 only feed their neighbours: 60 of 64 columns produce output);
+//   * applies clip_face_states only on a slow path.  Proof that this is exact: with s = minmod(c-m1, p1-c),
+//     |s| <= |RN(p1-c)| and s has the sign of p1-c, so c + s/2 lies between c and p1 in exact arithmetic
+//     (RN(p1-c)/2 < |p1-c| once the difference is inexact, and the difference is exact when it is small), and
+//     rounding is monotone, hence RN(c + s/2) is inside [min(c,p1), max(c,p1)], a subset of the clip interval
+//     [min(m1,c,p1), max(m1,c,p1)]; the same holds for p1 - s'/2.  The argument only fails when a difference
+//     overflowed or an input is non-finite, and then the face state itself is non-finite; that is what the slow
+//     path tests.  Selecting the upwind state before clamping is exact because both states get the same clamp.
+// Every other expression keeps the reference's operand order, and the build has no FMA contraction.
+//
+// Only faces whose four fluxes are all of the MUSCL kind (2 <= ii <= nx-1, 2 <= jj <= ny-1 in raw indices, valid
+// for u and v) are handled here; the first-order ring and the rows/columns next to it stay with k_rhs_simple.
+#pragma once
+#include "kernels_step.cuh"
+
+#define MARCH_WARPS 4
+#define MARCH_COLS 60 // output columns per warp (lanes 1..30, 2 columns each)
+
+// 0.5 * minmod(a, b)   (advection.cpp:10-12, then the 0.5 of :61-62)
+__device__ __forceinline__ double half_minmod(double a, double b) {
+    double s = (fabs(a) < fabs(b)) ? a : b;
+    s = (a * b <= 0.0) ? 0.0 : s;
+    return 0.5 * s;
+}
+
+// Flux through the face between c and p1 given the half slopes at c and p1 (see the header for the slow path).
+__device__ __forceinline__ double flux_shared(double m1, double c, double hc, double p1, double hp, double w) {
+    double qL = c + hc;
+    double qR = p1 - hp;
+    double q = (w > 0.0) ? qL : qR;
+    if (!finite_d(q)) {
+        double lo = min2(m1, min2(c, p1));
+        double hi = max2(m1, max2(c, p1));
+        q = clamp3(q, lo, hi);
+    }
+    return q * w;
+}
+
+struct MarchCol { // y-state of one column of one field while marching upwards
+    double qm1, q0, q1; // q(jj-1), q(jj), q(jj+1)
+    double dy0;         // q(jj+1) - q(jj)
+    double hs0;         // half slope at jj
+    double fym;         // y-flux through the face below jj
+};
+
+__device__ __forceinline__ double shfl_dn(double x) { return __shfl_down_sync(0xffffffffu, x, 1); }
+__device__ __forceinline__ double shfl_up(double x) { return __shfl_up_sync(0xffffffffu, x, 1); }
+
+// MODE as in k_rhs_simple.  Outputs: ii in [XA, XB], jj in [YA, YB]; each block row-strip covers RY rows.
+template <int MODE>
+__global__ void __launch_bounds__(32 * MARCH_WARPS)
+    k_rhs_march(Geom g, RhsConst k, const double *__restrict__ uin, const double *__restrict__ vin, double *uout,
+                double *vout, Scalars *sc, int XA, int XB, int YA, int YB, int RY) {
+    const int lane = threadIdx.x & 31;
+    const int wx = blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
+    const int X0 = XA - 2 + MARCH_COLS * wx; // raw column of lane 0's first column (odd => aligned double2)
+    if (X0 + 2 > XB) return;                 // whole warp outside
+    const int a = X0 + 2 * lane;             // this thread's columns: a, a+1
+    const int y0 = YA + blockIdx.y * RY;
+    const int y1 = min(y0 + RY - 1, YB);
+    const bool loadable = (a + 1 <= g.P - CFD_XOFF - 1);
+    const size_t P = g.P;
+    const double *pu = uin + gidx(g, a, 0);
+    const double *pv = vin + gidx(g, a, 0);
+    auto ld2 = [&](const double *base, int jj) -> double2 {
+        return loadable ? *reinterpret_cast<const double2 *>(base + (size_t)jj * P) : make_double2(0.0, 0.0);
+    };
+    const double dt = (MODE == 0) ? 0.0 : sc->dt;
+    const bool st_a = lane >= 1 && lane <= 30 && a >= XA && a <= XB;
+    const bool st_b = lane >= 1 && lane <= 30 && a + 1 >= XA && a + 1 <= XB;
+    int flag = 0;
+
+    MarchCol U[2], V[2];
+    // ---- prologue: rows y0-2 .. y0+1 -> state at jj = y0 (fym = flux through the face between y0-1 and y0)
+    {
+        double2 u0 = ld2(pu, y0 - 2), u1 = ld2(pu, y0 - 1), u2 = ld2(pu, y0), u3 = ld2(pu, y0 + 1);
+        double2 v0 = ld2(pv, y0 - 2), v1 = ld2(pv, y0 - 1), v2 = ld2(pv, y0), v3 = ld2(pv, y0 + 1);
+        auto init = [&](MarchCol &c, double q_2, double q_1, double q0, double q1, double w_below) {
+            double dm2 = q_1 - q_2, dm1 = q0 - q_1, d0 = q1 - q0;
+            double hsm1 = half_minmod(dm2, dm1);
+            c.hs0 = half_minmod(dm1, d0);
+            c.fym = flux_shared(q_2, q_1, hsm1, q0, c.hs0, w_below);
+            c.qm1 = q_1;
+            c.q0 = q0;
+            c.q1 = q1;
+            c.dy0 = d0;
+        };
+        // y-faces are carried by v(ii, jj) of the row below (advection.cpp:113, :275)
+        init(U[0], u0.x, u1.x, u2.x, u3.x, v1.x);
+        init(U[1], u0.y, u1.y, u2.y, u3.y, v1.y);
+        init(V[0], v0.x, v1.x, v2.x, v3.x, v1.x);
+        init(V[1], v0.y, v1.y, v2.y, v3.y, v1.y);
+    }
+
+    for (int jj = y0; jj <= y1; ++jj) {
+        const double2 nu = ld2(pu, jj + 2), nv = ld2(pv, jj + 2);
+        const size_t o = gidx(g, a, jj);
+        double2 au = make_double2(0.0, 0.0), av = make_double2(0.0, 0.0);
+        if (MODE == 2 && (st_a || st_b)) { // s.u / s.v, updated in place (only this thread touches these elements)
+            au = *reinterpret_cast<const double2 *>(uout + o);
+            av = *reinterpret_cast<const double2 *>(vout + o);
+        }
+        const double ua = U[0].q0, ub = U[1].q0, va = V[0].q0, vb = V[1].q0; // face velocities of this row
+
+        double du[2], dv[2];
+#pragma unroll
+        for (int f = 0; f < 2; ++f) { // f = 0: q = u, f = 1: q = v
+            MarchCol *C = f ? V : U;
+            const double q2a = f ? nv.x : nu.x, q2b = f ? nv.y : nu.y;
+            // ---- y direction: one new slope and one new flux per column (advection.cpp:85-114, :247-276)
+            double dy1a = q2a - C[0].q1, dy1b = q2b - C[1].q1;
+            double hs1a = half_minmod(C[0].dy0, dy1a), hs1b = half_minmod(C[1].dy0, dy1b);
+            double fya = flux_shared(C[0].qm1, C[0].q0, C[0].hs0, C[0].q1, hs1a, va);
+            double fyb = flux_shared(C[1].qm1, C[1].q0, C[1].hs0, C[1].q1, hs1b, vb);
+            // ---- x direction on row jj, shared across the warp (advection.cpp:52-81, :280-309)
+            const double qa = C[0].q0, qb = C[1].q0;
+            const double qa_n = shfl_dn(qa); // q(a+2)
+            const double qb_p = shfl_up(qb); // q(a-1)
+            double dxp = qa - qb_p, dxa = qb - qa, dxb = qa_n - qb;
+            double hsa = half_minmod(dxp, dxa), hsb = half_minmod(dxa, dxb);
+            const double hsa_n = shfl_dn(hsa);
+            double fxa = flux_shared(qb_p, qa, hsa, qb, hsb, ua);     // face a+1/2, carried by u(a, jj)
+            double fxb = flux_shared(qa, qb, hsb, qa_n, hsa_n, ub);   // face b+1/2, carried by u(b, jj)
+            const double fxb_p = shfl_up(fxb);                        // face a-1/2
+            // ---- flux divergence + diffusion (advection.cpp:117-118, diffusion.cpp:16-18)
+            double conva = (fxa - fxb_p) * k.idx + (fya - C[0].fym) * k.idy;
+            double convb = (fxb - fxa) * k.idx + (fyb - C[1].fym) * k.idy;
+            double lapa = (qb - 2.0 * qa + qb_p) * k.idx2 + (C[0].q1 - 2.0 * qa + C[0].qm1) * k.idy2;
+            double lapb = (qa_n - 2.0 * qb + qa) * k.idx2 + (C[1].q1 - 2.0 * qb + C[1].qm1) * k.idy2;
+            double da = -conva, db = -convb;
+            da = da + k.invRe * lapa;
+            db = db + k.invRe * lapb;
+            double *d = f ? dv : du;
+            d[0] = sanitize_val(da, flag);
+            d[1] = sanitize_val(db, flag);
+            // ---- rotate the y-state
+            C[0].qm1 = C[0].q0; C[0].q0 = C[0].q1; C[0].q1 = q2a; C[0].dy0 = dy1a; C[0].hs0 = hs1a; C[0].fym = fya;
+            C[1].qm1 = C[1].q0; C[1].q0 = C[1].q1; C[1].q1 = q2b; C[1].dy0 = dy1b; C[1].hs0 = hs1b; C[1].fym = fyb;
+        }
+        // ---- Runge-Kutta update + store (time_integrator.cpp:84-99, :122-143); qm1 now holds q(jj)
+        double2 ou, ov;
+        if (MODE == 0) {
+            ou = make_double2(du[0], du[1]);
+            ov = make_double2(dv[0], dv[1]);
+        } else if (MODE == 1) {
+            ou = make_double2(sanitize_val(ua + dt * du[0], flag), sanitize_val(ub + dt * du[1], flag));
+            ov = make_double2(sanitize_val(va + dt * dv[0], flag), sanitize_val(vb + dt * dv[1], flag));
+        } else {
+            ou = make_double2(sanitize_val(0.5 * (au.x + ua + dt * du[0]), flag),
+                              sanitize_val(0.5 * (au.y + ub + dt * du[1]), flag));
+            ov = make_double2(sanitize_val(0.5 * (av.x + va + dt * dv[0]), flag),
+                              sanitize_val(0.5 * (av.y + vb + dt * dv[1]), flag));
+        }
+        if (st_a && st_b) {
+            *reinterpret_cast<double2 *>(uout + o) = ou;
+            *reinterpret_cast<double2 *>(vout + o) = ov;
+        } else if (st_a) {
+            uout[o] = ou.x;
+            vout[o] = ov.x;
+        } else if (st_b) {
+            uout[o + 1] = ou.y;
+            vout[o + 1] = ov.y;
+        }
+    }
+    if (flag) sc->nonfinite_any = 1;
+}

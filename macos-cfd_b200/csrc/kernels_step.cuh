@@ -272,10 +272,10 @@ __device__ __forceinline__ double rhs_point(const double *qc, const double *uc, 
 template <int MODE>
 __global__ void __launch_bounds__(RHS_TX *RHS_TY)
     k_rhs_simple(Geom g, RhsConst k, const double *__restrict__ uin, const double *__restrict__ vin, double *uout,
-                 double *vout, Scalars *sc) {
+                 double *vout, Scalars *sc, int tx0, int ty0) {
     constexpr int S = RHS_TX + 4 + 1; // +1: odd stride
     __shared__ double us[(RHS_TY + 4) * S], vs[(RHS_TY + 4) * S];
-    const int x0 = 1 + blockIdx.x * RHS_TX, y0 = 1 + blockIdx.y * RHS_TY;
+    const int x0 = 1 + (tx0 + blockIdx.x) * RHS_TX, y0 = 1 + (ty0 + blockIdx.y) * RHS_TY; // tile offset: strips
     const int tid = threadIdx.y * RHS_TX + threadIdx.x;
     const int max_col = g.P - CFD_XOFF - 1, max_row = g.rows - CFD_YOFF - 1;
     for (int t = tid; t < (RHS_TY + 4) * (RHS_TX + 4); t += RHS_TX * RHS_TY) {
