@@ -108,11 +108,14 @@ def load_library(build: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    if build and (os.path.exists("/usr/local/cuda/bin/nvcc") or not os.path.exists(_build.LIB)):
-        _build.build()
-    if not os.path.exists(_build.LIB):
-        raise CfdError(-2, f"{_build.LIB} is missing and cannot be built: there is no CPU fallback")
-    L = C.CDLL(_build.LIB)
+    path = os.environ.get("CFD_B200_LIB")  # tuning experiments: an alternative build of the same sources
+    if not path:
+        if build and (os.path.exists("/usr/local/cuda/bin/nvcc") or not os.path.exists(_build.LIB)):
+            _build.build()
+        path = _build.LIB
+    if not os.path.exists(path):
+        raise CfdError(-2, f"{path} is missing and cannot be built: there is no CPU fallback")
+    L = C.CDLL(path)
     S = C.c_void_p
     L.cfd_b200_last_error.restype = C.c_char_p
     L.cfd_b200_create.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(S)]

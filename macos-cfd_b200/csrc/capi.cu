@@ -13,6 +13,7 @@
 #include "kernels_pressure.cuh"
 #include "kernels_step.cuh"
 #include "kernels_rhs_march.cuh"
+#include "kernels_rbgs_fused.cuh"
 
 namespace {
 
@@ -46,6 +47,7 @@ struct cfd_b200_solver {
     int rank = 0, nranks = 1;
     size_t n = 0; // doubles per field
     double *u = nullptr, *v = nullptr, *p = nullptr, *rhs = nullptr;
+    double *p_alt = nullptr; // ping-pong partner of p for the fused red-black smoother
     double *u1 = nullptr, *v1 = nullptr;           // TimeIntegrator work arrays (time_integrator.hpp:18-19)
     double *r = nullptr, *sA = nullptr, *sB = nullptr; // PressureSolver work arrays (pressure.hpp:29); z, Ap never stored
     double *scratch_u = nullptr, *scratch_v = nullptr; // stage-level entry points only (lazy)
@@ -213,6 +215,21 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
         if (pp->mg_mode != CFD_B200_MG_REFERENCE)
             return fail(CFD_B200_EUNSUPPORTED, "mg_mode=VCYCLE is not implemented yet");
         LAUNCH(s, k_solve_begin, 1, 1, s->d_sc);
+        if (s->variant != 0 && s->nranks == 1) { // fused smooth(): 4 colour passes + residual per launch, p ping-ponged
+            const int ntx = cdiv(g.nx, RB_TX), nty = cdiv(g.ny, RB_TY);
+            for (int vc = 0; vc < pp->vcycles; ++vc) {
+                if (g.denom_pow2)
+                    k_rbgs_fused<1, 1><<<ntx * nty, RB_THREADS, RB_SMEM, s->stream>>>(g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, pp->tol, ntx);
+                else
+                    k_rbgs_fused<0, 1><<<ntx * nty, RB_THREADS, RB_SMEM, s->stream>>>(g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, pp->tol, ntx);
+                s->launches++;
+                double *t = s->p;
+                s->p = s->p_alt;
+                s->p_alt = t;
+            }
+            LAUNCH(s, k_solve_finish, 1, 1, s->d_sc);
+            return 0;
+        }
         dim3 cblock(32, 8), cgrid(cdiv(cdiv(g.nx, 2), 32), cdiv(g.ny, 8));
         dim3 rgrid(cdiv(g.nx, 256), g.ny < 256 ? g.ny : 256);
         for (int vc = 0; vc < pp->vcycles; ++vc) {
@@ -353,7 +370,7 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
     int rc = 0;
     do {
         if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(CFD_B200_ECUDA, "stream create failed"); break; }
-        double **fields[] = {&s->u, &s->v, &s->p, &s->rhs, &s->u1, &s->v1, &s->r, &s->sA, &s->sB};
+        double **fields[] = {&s->u, &s->v, &s->p, &s->p_alt, &s->rhs, &s->u1, &s->v1, &s->r, &s->sA, &s->sB};
         for (double **f : fields)
             if ((rc = alloc_field(s, f)) != 0) break;
         if (rc) break;
@@ -362,6 +379,15 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
         if (cudaMallocHost(&s->h_sc, sizeof(Scalars)) != cudaSuccess) { rc = fail(CFD_B200_ENOMEM, "pinned alloc failed"); break; }
         memset(s->h_sc, 0, sizeof(Scalars));
         s->partials_n = 2 * 65536;
+        {
+            size_t tiles = (size_t)cdiv(nx, RB_TX) * cdiv(ny, RB_TY);
+            if (2 * tiles > s->partials_n) s->partials_n = 2 * tiles;
+        }
+        if (cudaFuncSetAttribute(k_rbgs_fused<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(k_rbgs_fused<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM) != cudaSuccess) {
+            rc = fail(CFD_B200_ECUDA, "cudaFuncSetAttribute(k_rbgs_fused) failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
         if (cudaMalloc(&s->partials, s->partials_n * sizeof(double)) != cudaSuccess) { rc = fail(CFD_B200_ENOMEM, "partials alloc failed"); break; }
         for (int i = 0; i < ST_COUNT; ++i)
             if (cudaEventCreate(&s->ev[i]) != cudaSuccess) { rc = fail(CFD_B200_ECUDA, "event create failed"); break; }
@@ -391,7 +417,7 @@ void cfd_b200_destroy(cfd_b200_solver *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    double *fields[] = {s->u, s->v, s->p, s->rhs, s->u1, s->v1, s->r, s->sA, s->sB, s->scratch_u, s->scratch_v, s->partials};
+    double *fields[] = {s->u, s->v, s->p, s->p_alt, s->rhs, s->u1, s->v1, s->r, s->sA, s->sB, s->scratch_u, s->scratch_v, s->partials};
     for (double *f : fields)
         if (f) cudaFree(f);
     if (s->d_sc) cudaFree(s->d_sc);

@@ -10,7 +10,7 @@
 //   * gives each thread 2 adjacent columns (one aligned double2 per row and field) and exchanges the x-neighbours'
 //     value / slope / flux with 4 warp shuffles per field: each x-flux and x-slope is computed once per warp
 //     (lanes 0 and 31 only feed their neighbours: 60 of 64 columns produce output);
-//   * applies clip_face_states only on a slow path.  Proof that this is exact: with s = minmod(c-m1, p1-c),
+//   * applies clip_face_states only on a slow path (one finiteness test per derivative, not per flux).  Proof that this is exact: with s = minmod(c-m1, p1-c),
 //     |s| <= |RN(p1-c)| and s has the sign of p1-c, so c + s/2 lies between c and p1 in exact arithmetic
 //     (RN(p1-c)/2 < |p1-c| once the difference is inexact, and the difference is exact when it is small), and
 //     rounding is monotone, hence RN(c + s/2) is inside [min(c,p1), max(c,p1)], a subset of the clip interval
@@ -25,6 +25,9 @@
 #include "kernels_step.cuh"
 
 #define MARCH_WARPS 4
+#ifndef MARCH_MINBLOCKS
+#define MARCH_MINBLOCKS 4 // resident blocks per SM the register allocator must allow (tuned on B200, see profiles/)
+#endif
 #define MARCH_COLS 60 // output columns per warp (lanes 1..30, 2 columns each)
 
 // 0.5 * minmod(a, b)   (advection.cpp:10-12, then the 0.5 of :61-62)
@@ -34,17 +37,21 @@ __device__ __forceinline__ double half_minmod(double a, double b) {
     return 0.5 * s;
 }
 
-// Flux through the face between c and p1 given the half slopes at c and p1 (see the header for the slow path).
-__device__ __forceinline__ double flux_shared(double m1, double c, double hc, double p1, double hp, double w) {
+// Flux through the face between c and p1 given the half slopes at c and p1.  No clip here: a face state that the
+// clip could change is non-finite (header), a non-finite state makes the flux, the flux difference and finally the
+// derivative non-finite, and the caller recomputes every non-finite derivative with the reference formula (rhs_point).
+__device__ __forceinline__ double flux_shared(double c, double hc, double p1, double hp, double w) {
     double qL = c + hc;
     double qR = p1 - hp;
-    double q = (w > 0.0) ? qL : qR;
-    if (!finite_d(q)) {
-        double lo = min2(m1, min2(c, p1));
-        double hi = max2(m1, max2(c, p1));
-        q = clamp3(q, lo, hi);
-    }
-    return q * w;
+    return ((w > 0.0) ? qL : qR) * w;
+}
+
+// Out-of-line slow path: the reference formula for one interior face, read straight from memory (keeps the hot
+// loop's register budget free of the clip logic).
+__device__ __noinline__ double rhs_point_slow(const double *q, const double *u, const double *v, int S, double idx,
+                                              double idy, double idx2, double idy2, double invRe) {
+    RhsConst k{idx, idy, idx2, idy2, invRe};
+    return rhs_point(q, u, v, S, 0, 0, k);
 }
 
 struct MarchCol { // y-state of one column of one field while marching upwards
@@ -59,7 +66,7 @@ __device__ __forceinline__ double shfl_up(double x) { return __shfl_up_sync(0xff
 
 // MODE as in k_rhs_simple.  Outputs: ii in [XA, XB], jj in [YA, YB]; each block row-strip covers RY rows.
 template <int MODE>
-__global__ void __launch_bounds__(32 * MARCH_WARPS)
+__global__ void __launch_bounds__(32 * MARCH_WARPS, MARCH_MINBLOCKS)
     k_rhs_march(Geom g, RhsConst k, const double *__restrict__ uin, const double *__restrict__ vin, double *uout,
                 double *vout, Scalars *sc, int XA, int XB, int YA, int YB, int RY) {
     const int lane = threadIdx.x & 31;
@@ -90,7 +97,7 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS)
             double dm2 = q_1 - q_2, dm1 = q0 - q_1, d0 = q1 - q0;
             double hsm1 = half_minmod(dm2, dm1);
             c.hs0 = half_minmod(dm1, d0);
-            c.fym = flux_shared(q_2, q_1, hsm1, q0, c.hs0, w_below);
+            c.fym = flux_shared(q_1, hsm1, q0, c.hs0, w_below);
             c.qm1 = q_1;
             c.q0 = q0;
             c.q1 = q1;
@@ -103,6 +110,7 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS)
         init(V[1], v0.y, v1.y, v2.y, v3.y, v1.y);
     }
 
+#pragma unroll 1
     for (int jj = y0; jj <= y1; ++jj) {
         const double2 nu = ld2(pu, jj + 2), nv = ld2(pv, jj + 2);
         const size_t o = gidx(g, a, jj);
@@ -121,8 +129,8 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS)
             // ---- y direction: one new slope and one new flux per column (advection.cpp:85-114, :247-276)
             double dy1a = q2a - C[0].q1, dy1b = q2b - C[1].q1;
             double hs1a = half_minmod(C[0].dy0, dy1a), hs1b = half_minmod(C[1].dy0, dy1b);
-            double fya = flux_shared(C[0].qm1, C[0].q0, C[0].hs0, C[0].q1, hs1a, va);
-            double fyb = flux_shared(C[1].qm1, C[1].q0, C[1].hs0, C[1].q1, hs1b, vb);
+            double fya = flux_shared(C[0].q0, C[0].hs0, C[0].q1, hs1a, va);
+            double fyb = flux_shared(C[1].q0, C[1].hs0, C[1].q1, hs1b, vb);
             // ---- x direction on row jj, shared across the warp (advection.cpp:52-81, :280-309)
             const double qa = C[0].q0, qb = C[1].q0;
             const double qa_n = shfl_dn(qa); // q(a+2)
@@ -130,8 +138,8 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS)
             double dxp = qa - qb_p, dxa = qb - qa, dxb = qa_n - qb;
             double hsa = half_minmod(dxp, dxa), hsb = half_minmod(dxa, dxb);
             const double hsa_n = shfl_dn(hsa);
-            double fxa = flux_shared(qb_p, qa, hsa, qb, hsb, ua);     // face a+1/2, carried by u(a, jj)
-            double fxb = flux_shared(qa, qb, hsb, qa_n, hsa_n, ub);   // face b+1/2, carried by u(b, jj)
+            double fxa = flux_shared(qa, hsa, qb, hsb, ua);     // face a+1/2, carried by u(a, jj)
+            double fxb = flux_shared(qb, hsb, qa_n, hsa_n, ub);   // face b+1/2, carried by u(b, jj)
             const double fxb_p = shfl_up(fxb);                        // face a-1/2
             // ---- flux divergence + diffusion (advection.cpp:117-118, diffusion.cpp:16-18)
             double conva = (fxa - fxb_p) * k.idx + (fya - C[0].fym) * k.idy;
@@ -141,9 +149,13 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS)
             double da = -conva, db = -convb;
             da = da + k.invRe * lapa;
             db = db + k.invRe * lapb;
+            // slow path (overflow / non-finite input only): the reference formula, clip included, straight from memory
+            const double *qg = (f ? vin : uin) + o;
+            if (st_a && !finite_d(da)) da = rhs_point_slow(qg, uin + o, vin + o, (int)P, k.idx, k.idy, k.idx2, k.idy2, k.invRe);
+            if (st_b && !finite_d(db)) db = rhs_point_slow(qg + 1, uin + o + 1, vin + o + 1, (int)P, k.idx, k.idy, k.idx2, k.idy2, k.invRe);
             double *d = f ? dv : du;
-            d[0] = sanitize_val(da, flag);
-            d[1] = sanitize_val(db, flag);
+            d[0] = st_a ? sanitize_val(da, flag) : 0.0; // lanes that only feed their neighbours hold no result
+            d[1] = st_b ? sanitize_val(db, flag) : 0.0;
             // ---- rotate the y-state
             C[0].qm1 = C[0].q0; C[0].q0 = C[0].q1; C[0].q1 = q2a; C[0].dy0 = dy1a; C[0].hs0 = hs1a; C[0].fym = fya;
             C[1].qm1 = C[1].q0; C[1].q0 = C[1].q1; C[1].q1 = q2b; C[1].dy0 = dy1b; C[1].hs0 = hs1b; C[1].fym = fyb;

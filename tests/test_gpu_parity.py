@@ -98,7 +98,7 @@ def test_stage_kernels_bit_exact(cfd, port, nx, ny, Lx, Ly, variant):
     u, v, p = rand_fields(nx, ny, nx * 1000 + ny)
     u[3, 2] = 0.0
     v[2, 2] = -0.0
-    if nx > 100:  # zeros, signed zeros, plateaus and huge values inside the marching kernel's region
+    if nx > 100 and ny > 100:  # zeros, signed zeros, plateaus and huge values inside the marching kernel's region
         u[40:44, 50:70] = 0.0
         v[40:44, 50:70] = -0.0
         u[60:64, 80:90] = 0.25
@@ -131,7 +131,8 @@ def test_stage_kernels_bit_exact(cfd, port, nx, ny, Lx, Ly, variant):
     grhs = s.download()[3]
     assert same(grhs[1:-1, 1:-1], rhs[1:-1, 1:-1]), nbad(grhs, rhs)
     # diagnostics (reductions: tolerance)
-    assert abs(s.divergence_l2() - port.divergence_l2(nx, ny, Lx, Ly, u, v)) <= 1e-13 * abs(s.divergence_l2())
+    gd, od = s.divergence_l2(), port.divergence_l2(nx, ny, Lx, Ly, u, v)
+    assert gd == od or abs(gd - od) <= 1e-13 * abs(od)  # (the 1e300 sentinels make both inf)
     assert s.max_velocity() == port.max_velocity(nx, ny, Lx, Ly, u, v)
     # subtract_grad_p (p(0,0) pinned as in TimeIntegrator::step)
     p0 = p.copy()
