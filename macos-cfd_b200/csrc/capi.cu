@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -58,6 +59,8 @@ struct cfd_b200_solver {
     cudaStream_t stream = nullptr;
     long long launches = 0;
     int variant = 1;
+    bool cfl_cached = false;   // umax/vmax of the current device State are already in d_sc (from the last step)
+    cfd_b200_bc last_bc{};
     int profiling = 0;
     cudaEvent_t ev[ST_COUNT] = {};
     bool ev_valid = false;
@@ -116,6 +119,14 @@ BcD to_bcd(const cfd_b200_bc *b) {
     return d;
 }
 
+bool bc_equal(const cfd_b200_bc &a, const cfd_b200_bc &b) { // field by field: the structs carry padding bytes
+    auto side = [](const cfd_b200_bc_side &x, const cfd_b200_bc_side &y) {
+        return x.type == y.type && x.moving == y.moving && x.inflow_u == y.inflow_u && x.inflow_v == y.inflow_v;
+    };
+    return side(a.left, b.left) && side(a.right, b.right) && side(a.bottom, b.bottom) && side(a.top, b.top) &&
+           a.jet_center == b.jet_center && a.jet_width == b.jet_width;
+}
+
 void stage_mark(cfd_b200_solver *s, int st) {
     if (s->profiling) cudaEventRecord(s->ev[st], s->stream);
 }
@@ -129,8 +140,15 @@ void enqueue_bc(cfd_b200_solver *s, const BcD &bc, double *u, double *v, double 
 
 void enqueue_cfl(cfd_b200_solver *s, double Re, double CFL, double dt_override, int cfl_only) {
     const Geom &g = s->g;
-    dim3 grid(cdiv(g.P / 2, 256), g.ny + 1 < 64 ? g.ny + 1 : 64);
-    LAUNCH(s, k_absmax, grid, 256, g, s->u, s->v, s->d_sc);
+    if (!s->cfl_cached) {
+        // max|u|, max|v| of compute_cfl.  Skipped when the previous step's post-projection divergence kernel already
+        // left them in d_sc: the BC pass in between only rewrites ring faces with the values they already hold (or,
+        // for periodic sides, swaps two columns), so the maxima over all faces are unchanged.
+        cudaMemsetAsync(&s->d_sc->umax_bits, 0, 2 * sizeof(unsigned long long), s->stream);
+        dim3 grid(cdiv(g.P / 2, 256), g.ny + 1 < 64 ? g.ny + 1 : 64);
+        LAUNCH(s, k_absmax, grid, 256, g, s->u, s->v, s->d_sc);
+    }
+    s->cfl_cached = false;
     // (slabs: max-allreduce of umax/vmax goes here)
     LAUNCH(s, k_dt, 1, 1, g, Re, CFL, dt_override, s->d_sc, cfl_only);
 }
@@ -176,14 +194,14 @@ dim3 row_grid(const cfd_b200_solver *s, int ncols, int nrows, int *rows_per_bloc
     return dim3(gx, cdiv(nrows, rpb));
 }
 
-void enqueue_divergence(cfd_b200_solver *s, int pre, int want_sum) {
+void enqueue_divergence(cfd_b200_solver *s, int pre, int want_sum, int want_max = 0) {
     const Geom &g = s->g;
     int rpb = 4;
     dim3 grid = row_grid(s, g.nx, g.ny, &rpb);
     if (pre)
-        LAUNCH(s, k_divergence<1>, grid, 256, g, s->u, s->v, s->rhs, s->p, s->d_sc, s->partials, want_sum, rpb);
+        LAUNCH(s, k_divergence<1>, grid, 256, g, s->u, s->v, s->rhs, s->p, s->d_sc, s->partials, want_sum, rpb, 0);
     else
-        LAUNCH(s, k_divergence<0>, grid, 256, g, s->u, s->v, s->rhs, (double *)nullptr, s->d_sc, s->partials, want_sum, rpb);
+        LAUNCH(s, k_divergence<0>, grid, 256, g, s->u, s->v, s->rhs, (double *)nullptr, s->d_sc, s->partials, want_sum, rpb, want_max);
 }
 
 int pcg_grid(const cfd_b200_solver *s, int ntiles) {
@@ -250,7 +268,7 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
 void enqueue_project(cfd_b200_solver *s, const Scalars *dt_src, double dt_arg) {
     const Geom &g = s->g;
     int rpb = 4;
-    dim3 grid = row_grid(s, g.nx + 1, g.ny + 1, &rpb);
+    dim3 grid = row_grid(s, cdiv(g.nx + 1, 2), g.ny + 1, &rpb);
     LAUNCH(s, k_project, grid, 256, g, s->u, s->v, s->p, dt_src, dt_arg, s->d_sc, rpb);
 }
 
@@ -263,6 +281,8 @@ int enqueue_step(cfd_b200_solver *s, const cfd_b200_bc *bc_in, double Re, double
     if (both_bt && s->nranks > 1)
         return fail(CFD_B200_EUNSUPPORTED, "bottom/top Periodic is not supported across row slabs");
     const double invRe = 1.0 / Re; // "1.0 / Re" at time_integrator.cpp:76
+    if (!bc_equal(s->last_bc, *bc_in) || s->variant == 0 || s->nranks > 1) s->cfl_cached = false;
+    s->last_bc = *bc_in;
     stage_mark(s, ST_BC0);
     enqueue_bc(s, bc, s->u, s->v, s->p, 0); // :51-53
     stage_mark(s, ST_CFL);
@@ -285,7 +305,8 @@ int enqueue_step(cfd_b200_solver *s, const cfd_b200_bc *bc_in, double Re, double
     stage_mark(s, ST_BC3);
     enqueue_bc(s, bc, s->u, s->v, s->p, 1); // :205-207
     stage_mark(s, ST_DIV2);
-    enqueue_divergence(s, 0, 1); // :210-220
+    enqueue_divergence(s, 0, 1, 1); // :210-220 (+ max|u|, max|v| for the next step's compute_cfl)
+    s->cfl_cached = true;
     LAUNCH(s, k_sanitize_if, s->sm_count * 4, 256, g, s->p, s->d_sc); // :236
     stage_mark(s, ST_END);
     s->ev_valid = s->profiling != 0;
@@ -433,6 +454,7 @@ int cfd_b200_upload(cfd_b200_solver *s, const double *u, const double *v, const 
     CU(cudaSetDevice(s->device));
     const Geom &g = s->g;
     int rc = 0;
+    if (u || v) s->cfl_cached = false;
     if (u && (rc = copy_field(s, s->u, const_cast<double *>(u), g.nx + 3, g.ny + 2, true))) return rc;
     if (v && (rc = copy_field(s, s->v, const_cast<double *>(v), g.nx + 2, g.ny + 3, true))) return rc;
     if (p && (rc = copy_field(s, s->p, const_cast<double *>(p), g.nx + 2, g.ny + 2, true))) return rc;
@@ -531,6 +553,7 @@ int cfd_b200_max_velocity(cfd_b200_solver *s, double *out) {
 int cfd_b200_apply_bc(cfd_b200_solver *s, const cfd_b200_bc *bc, int which) {
     if (!s || !bc) return fail(CFD_B200_EINVAL, "NULL argument");
     CU(cudaSetDevice(s->device));
+    s->cfl_cached = false;
     enqueue_bc(s, to_bcd(bc), (which & 1) ? s->u : nullptr, (which & 2) ? s->v : nullptr, (which & 4) ? s->p : nullptr, 0);
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
@@ -589,6 +612,7 @@ int cfd_b200_pressure_solve(cfd_b200_solver *s, const cfd_b200_params *pp, doubl
 int cfd_b200_subtract_grad_p(cfd_b200_solver *s, double dt) {
     if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
     CU(cudaSetDevice(s->device));
+    s->cfl_cached = false;
     enqueue_project(s, nullptr, dt);
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());

@@ -16,44 +16,58 @@
 #pragma once
 #include "common.cuh"
 
-#define RB_TX 116          // output columns per tile (even: keeps double2 alignment)
-#define RB_TY 54           // output rows per tile
+// Tile geometry.  A thread owns RB_M x RB_N slots (a slot = aligned pair of columns): rows ly = RB_M*warp + m,
+// column pairs k = lane + 32 n.  Default: 128 x 64 tile, 512 threads (2 blocks/SM); -DRB_N=1: 64 x 64 tile, 256 threads.
+#ifndef RB_N
+#define RB_N 2
+#endif
+#ifndef RB_M
+#define RB_M (RB_N == 2 ? 4 : 8)
+#endif
+#ifndef RB_WARPS
+#define RB_WARPS (RB_N == 2 ? 16 : 8)
+#endif
 #define RB_HX 6            // x halo (5 needed; 6 keeps the tile origin on an even device column)
 #define RB_HY 5            // y halo
-#define RB_W (RB_TX + 2 * RB_HX) // 128
-#define RB_H (RB_TY + 2 * RB_HY) // 64
-#define RB_K (RB_W / 2)          // 64 points per class per row
-#define RB_THREADS 512
-#define RB_SMEM (2 * RB_H * RB_K * 8)
+#define RB_W (64 * RB_N)            // columns of the shared tile
+#define RB_H (RB_M * RB_WARPS)      // rows of the shared tile
+#define RB_TX (RB_W - 2 * RB_HX)    // output columns per tile (even: keeps double2 alignment)
+#define RB_TY (RB_H - 2 * RB_HY)    // output rows per tile
+#define RB_K (RB_W / 2)             // points per class per row
+#define RB_THREADS (32 * RB_WARPS)
+#define RB_MINBLOCKS (RB_N == 2 ? 2 : 4)
+#define RB_PAD (RB_K + 8)             // doubles of padding before and after the two class arrays
+#define RB_SMEM ((2 * RB_H * RB_K + 2 * RB_PAD) * 8)
 
-// One update of the point in slot (M, n), column parity E, during pass PS.  Everything that selects registers or
-// shared-memory offsets is a compile-time constant; the only runtime test is the point's margin.
-template <int POW2, int PS, int M, int E>
-__device__ __forceinline__ void rb_update(const Geom &g, double *sm, int warp, int lane, int n, int mg, double rvv,
-                                          double *pout, size_t o, int &pflag) {
+// One update of the point (ly, k) with row parity LYP and column parity E during pass PS.  Everything that selects
+// registers or shared-memory offsets is a compile-time constant; the only runtime test is the point's margin.
+template <int POW2, int PS, int LYP, int E>
+__device__ __forceinline__ void rb_update(const Geom &g, double *sm, int ly, int k, int mg, double rvv, double *pout,
+                                          size_t o, int &pflag) {
+    // Branch-free: the update is always computed (shared memory is padded, so the reads of points outside the pass
+    // region are harmless) and only the stores are predicated -- a thread's 8 updates of a pass can then overlap.
     // pass PS updates the tile grown by 4-PS: margin (distance inside the output tile, negative outside) >= PS-4
-    if (mg < PS - 4) return;
-    constexpr int LYP = M & 1;              // parity of the local row (ly = 4*warp + M)
-    constexpr int CLS = (E + LYP) & 1;      // checkerboard class of this point
-    const int ly = 4 * warp + M, k = lane + 32 * n;
+    constexpr int CLS = (E + LYP) & 1; // checkerboard class of this point
     const double *oth = sm + ((CLS ^ 1) * RB_H + ly) * RB_K + k;
     const double pl = oth[E - 1], pr = oth[E], pb = oth[-RB_K], pt = oth[RB_K];
     const double sum = (pr + pl) * g.idx2 + (pt + pb) * g.idy2;
     const double x = POW2 ? (rvv + sum) * g.inv_denom : (rvv + sum) / g.denom;
-    sm[(CLS * RB_H + ly) * RB_K + k] = fin0(x);
+    const bool fin = finite_d(x);
+    if (mg >= PS - 4) sm[(CLS * RB_H + ly) * RB_K + k] = fin ? x : 0.0;
     if (PS >= 2 && mg >= 0) { // last update of a point of the output tile: the value smooth() leaves in p
         pout[o] = x;
-        if (!finite_d(x)) pflag = 1;
+        pflag |= fin ? 0 : 1;
     }
 }
 
 // PAR0 = colour of local class 0, i.e. (Xe + Ye + j0) & 1.  Xe + Ye is odd for every tile (RB_TX, RB_TY even,
 // RB_HX + RB_HY odd), so PAR0 = (1 + j0) & 1 is one constant per launch.
 template <int POW2, int PAR0>
-__global__ void __launch_bounds__(RB_THREADS, 2)
+__global__ void __launch_bounds__(RB_THREADS, RB_MINBLOCKS)
     k_rbgs_fused(Geom g, const double *__restrict__ pin, double *__restrict__ pout, const double *__restrict__ rhs,
                  Scalars *sc, double *partials, double tol, int ntx) {
-    extern __shared__ double sm[]; // [2][RB_H][RB_K]
+    extern __shared__ double sm_raw[];
+    double *sm = sm_raw + RB_PAD; // [2][RB_H][RB_K], padded on both sides
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ty = blockIdx.x / ntx, tx = blockIdx.x - ty * ntx;
     const int X0 = 1 + tx * RB_TX, Y0 = 1 + ty * RB_TY; // first output cell (raw)
@@ -65,24 +79,24 @@ __global__ void __launch_bounds__(RB_THREADS, 2)
     // ---- load: thread (warp, lane) owns slots (ly = 4*warp + m, k = lane + 32 n), m < 4, n < 2; a slot is the
     //      aligned pair of local columns (2k, 2k+1).  rhs stays in registers for all passes; mg = margin of a point:
     //      how far inside the output tile it is (negative = in the halo), -100 when it is not an interior cell.
-    double rv[4][2][2]; // [m][n][e] : e = local column parity
-    int mgx[2][2], mgy[4]; // margin = min(mgx[n][e], mgy[m])
-    const size_t o00 = gidx(g, Xe + 2 * lane, Ye + 4 * warp); // element offset of slot (m = 0, n = 0)
+    double rv[RB_M][RB_N][2]; // [m][n][e] : e = local column parity
+    int mgx[RB_N][2], mgy[RB_M]; // margin = min(mgx[n][e], mgy[m])
+    const size_t o00 = gidx(g, Xe + 2 * lane, Ye + RB_M * warp); // element offset of slot (m = 0, n = 0)
     // A tile whose halo stays inside the interior needs no ghost / domain logic at all (block-uniform branch).
     const bool edge = Xe < 1 || Xe + RB_W - 1 > g.nx || Ye < 1 || Ye + RB_H - 1 > g.ny || done;
 #pragma unroll
-    for (int n = 0; n < 2; ++n)
+    for (int n = 0; n < RB_N; ++n)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int lx = 2 * (lane + 32 * n) + e, ci = Xe + lx;
             mgx[n][e] = (!edge || (ci >= 1 && ci <= g.nx)) ? min(lx - RB_HX, RB_HX + RB_TX - 1 - lx) : -100;
         }
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-        const int ly = 4 * warp + m, jj = Ye + ly;
+    for (int m = 0; m < RB_M; ++m) {
+        const int ly = RB_M * warp + m, jj = Ye + ly;
         mgy[m] = (!edge || (jj >= 1 && jj <= g.ny)) ? min(ly - RB_HY, RB_HY + RB_TY - 1 - ly) : -100;
 #pragma unroll
-        for (int n = 0; n < 2; ++n) {
+        for (int n = 0; n < RB_N; ++n) {
             const int k = lane + 32 * n, ii = Xe + 2 * k;
             const size_t o = o00 + (size_t)m * g.P + 64 * n;
             double2 pv = make_double2(0.0, 0.0), rr = make_double2(0.0, 0.0);
@@ -120,12 +134,16 @@ __global__ void __launch_bounds__(RB_THREADS, 2)
 #define RB_PASS(PS)                                                                                                  \
     {                                                                                                                \
         constexpr int CLS = ((PS) & 1) ^ PAR0;                                                                       \
-        _Pragma("unroll") for (int n = 0; n < 2; ++n) {                                                              \
-            const size_t on = o00 + 64 * n;                                                                          \
-            rb_update<POW2, PS, 0, (CLS + 0) & 1>(g, sm, warp, lane, n, min(mgx[n][(CLS + 0) & 1], mgy[0]), rv[0][n][(CLS + 0) & 1], pout, on + ((CLS + 0) & 1), pflag);               \
-            rb_update<POW2, PS, 1, (CLS + 1) & 1>(g, sm, warp, lane, n, min(mgx[n][(CLS + 1) & 1], mgy[1]), rv[1][n][(CLS + 1) & 1], pout, on + g.P + ((CLS + 1) & 1), pflag);         \
-            rb_update<POW2, PS, 2, (CLS + 0) & 1>(g, sm, warp, lane, n, min(mgx[n][(CLS + 0) & 1], mgy[2]), rv[2][n][(CLS + 0) & 1], pout, on + 2 * (size_t)g.P + ((CLS + 0) & 1), pflag); \
-            rb_update<POW2, PS, 3, (CLS + 1) & 1>(g, sm, warp, lane, n, min(mgx[n][(CLS + 1) & 1], mgy[3]), rv[3][n][(CLS + 1) & 1], pout, on + 3 * (size_t)g.P + ((CLS + 1) & 1), pflag); \
+        constexpr int E0 = CLS, E1 = CLS ^ 1; /* column parity of the class in even / odd rows */                    \
+        _Pragma("unroll") for (int m2 = 0; m2 < RB_M / 2; ++m2) {                                                    \
+            _Pragma("unroll") for (int n = 0; n < RB_N; ++n) {                                                       \
+                const int k = lane + 32 * n, ly = RB_M * warp + 2 * m2;                                              \
+                const size_t on = o00 + 64 * n + (size_t)(2 * m2) * g.P;                                             \
+                rb_update<POW2, PS, 0, E0>(g, sm, ly, k, min(mgx[n][E0], mgy[2 * m2]), rv[2 * m2][n][E0], pout,      \
+                                           on + E0, pflag);                                                          \
+                rb_update<POW2, PS, 1, E1>(g, sm, ly + 1, k, min(mgx[n][E1], mgy[2 * m2 + 1]), rv[2 * m2 + 1][n][E1], \
+                                           pout, on + g.P + E1, pflag);                                              \
+            }                                                                                                        \
         }                                                                                                            \
         __syncthreads();                                                                                             \
     }
@@ -137,21 +155,21 @@ __global__ void __launch_bounds__(RB_THREADS, 2)
 
     // ---- residual (pressure.cpp:96-110): r = fin0(rhs) - fin0(L p), sum of fin0(r)^2 over the output tile
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-        const int ly = 4 * warp + m;
+    for (int m = 0; m < RB_M; ++m) {
+        const int ly = RB_M * warp + m;
 #pragma unroll
-        for (int n = 0; n < 2; ++n) {
+        for (int n = 0; n < RB_N; ++n) {
             const int k = lane + 32 * n;
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                if (min(mgx[n][e], mgy[m]) < 0) continue;
+                const bool inside = min(mgx[n][e], mgy[m]) >= 0;
                 const int c = (e + m) & 1; // class of this point
                 const double *own = sm + (c * RB_H + ly) * RB_K + k, *oth = sm + ((c ^ 1) * RB_H + ly) * RB_K + k;
                 const double cc = own[0], l = oth[e - 1], r = oth[e], b = oth[-RB_K], t = oth[RB_K];
                 const double Ap = (r - 2.0 * cc + l) * g.idx2 + (t - 2.0 * cc + b) * g.idy2;
                 double res = rv[m][n][e] - Ap;
                 if (!finite_d(res)) res = fin0(rv[m][n][e] - fin0(Ap)); // fin0(rhs) - fin0(Ap), then dot()'s guard
-                acc[0] += res * res;
+                acc[0] += inside ? res * res : 0.0;
             }
         }
     }

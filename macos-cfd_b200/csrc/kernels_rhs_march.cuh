@@ -110,9 +110,15 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS, MARCH_MINBLOCKS)
         init(V[1], v0.y, v1.y, v2.y, v3.y, v1.y);
     }
 
+    // rows are requested one iteration ahead of their use (ncu: the loop was stalled on its own loads)
+    double2 pre_u = ld2(pu, y0 + 2), pre_v = ld2(pv, y0 + 2);
 #pragma unroll 1
     for (int jj = y0; jj <= y1; ++jj) {
-        const double2 nu = ld2(pu, jj + 2), nv = ld2(pv, jj + 2);
+        const double2 nu = pre_u, nv = pre_v;
+        if (jj < y1) {
+            pre_u = ld2(pu, jj + 3);
+            pre_v = ld2(pv, jj + 3);
+        }
         const size_t o = gidx(g, a, jj);
         double2 au = make_double2(0.0, 0.0), av = make_double2(0.0, 0.0);
         if (MODE == 2 && (st_a || st_b)) { // s.u / s.v, updated in place (only this thread touches these elements)

@@ -325,9 +325,10 @@ __global__ void __launch_bounds__(RHS_TX *RHS_TY)
 template <int PRE>
 __global__ void __launch_bounds__(256)
     k_divergence(Geom g, const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ rhs,
-                 double *p, Scalars *sc, double *partials, int want_sum, int rpb) {
+                 double *p, Scalars *sc, double *partials, int want_sum, int rpb, int want_max) {
     const int ii = 1 + blockIdx.x * blockDim.x + threadIdx.x;
     double acc[1] = {0.0};
+    double mu = 0.0, mv = 0.0; // max |u|, max |v| over all faces (compute_cfl of the NEXT step, metrics.cpp:8-24)
     if (ii <= g.nx) {
         const int jbase = 1 + blockIdx.y * rpb; // contiguous chunk of rpb rows per block
         const double inv_dt = PRE ? sc->inv_dt : 1.0;
@@ -336,8 +337,15 @@ __global__ void __launch_bounds__(256)
             const int jj = jbase + r;
             if (jj > g.ny) break;
             const size_t o = gidx(g, ii, jj);
-            double uR = fin0(u[o + 1]), uL = fin0(u[o]);
-            double vT = fin0(v[o + g.P]), vB = fin0(v[o]);
+            const double uRr = u[o + 1], uLr = u[o], vTr = v[o + g.P], vBr = v[o];
+            if (!PRE && want_max) {
+                mu = max2(mu, fabs(uLr));
+                if (ii == g.nx) mu = max2(mu, fabs(uRr));
+                mv = max2(mv, fabs(vBr));
+                if (jj == g.ny && g.top) mv = max2(mv, fabs(vTr));
+            }
+            double uR = fin0(uRr), uL = fin0(uLr);
+            double vT = fin0(vTr), vB = fin0(vBr);
             double divx = (uR - uL) * g.idx;
             double divy = (vT - vB) * g.idy;
             double d = fin0(divx + divy);
@@ -348,6 +356,10 @@ __global__ void __launch_bounds__(256)
     }
     if (PRE && p && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && g.j0 == 0)
         p[gidx(g, 1, 1)] = 0.0; // s.p(0,0) = 0 before the solve, time_integrator.cpp:186
+    if (!PRE && want_max) {
+        block_max_to_global(mu, &sc->umax_bits);
+        block_max_to_global(mv, &sc->vmax_bits);
+    }
     if (want_sum) {
         const double ncell = (double)(g.nx * g.ny_glob); // "(g.nx * g.ny)" is an int product in the reference
         grid_sum<1>(acc, partials, &sc->ticket[0], [=](double(&t)[1]) {
@@ -368,33 +380,60 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     k_project(Geom g, double *__restrict__ u, double *__restrict__ v, double *p, const Scalars *sc, double dt_arg,
               Scalars *flags, int rpb) {
-    const int ii = 1 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (ii > g.nx + 1) return;
+    // One thread = two adjacent columns (aligned double2) marching up rpb rows; the p pair of the row below is
+    // carried in registers, p(ii-1) comes from the left lane.
+    const int ii = 1 + 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const bool active = ii <= g.nx + 1;
     const double dt = sc ? sc->dt : dt_arg;
     const int jbase = 1 + blockIdx.y * rpb;
     const int JYv = v_rows(g);
     const bool pin_here = (g.j0 == 0);
+    const bool u_b = ii + 1 <= g.nx + 1, v_a = ii <= g.nx, v_b = ii + 1 <= g.nx; // which faces of the pair exist
     int flag = 0;
-#pragma unroll 4
+    double2 pb = make_double2(0.0, 0.0);
+    if (active) pb = *reinterpret_cast<const double2 *>(p + gidx(g, ii, jbase - 1));
+    if (pin_here && jbase - 1 == 1 && ii == 1) pb.x = 0.0;
+#pragma unroll 2
     for (int r = 0; r < rpb; ++r) {
         const int jj = jbase + r;
         if (jj > JYv) break;
         const size_t o = gidx(g, ii, jj);
-        double pc = p[o], pl = p[o - 1], pb = p[o - g.P];
-        if (pin_here) {
-            if (jj == 1 && ii == 1) pc = 0.0;
-            if (jj == 1 && ii == 2) pl = 0.0;
-            if (jj == 2 && ii == 1) pb = 0.0;
+        double2 pc = make_double2(0.0, 0.0);
+        if (active) pc = *reinterpret_cast<const double2 *>(p + o);
+        if (pin_here && jj == 1 && ii == 1) pc.x = 0.0; // s.p(0,0) = 0 after the solve, time_integrator.cpp:188
+        double pl = __shfl_up_sync(0xffffffffu, pc.y, 1);
+        if ((threadIdx.x & 31) == 0 && active) {
+            pl = p[o - 1];
+            if (pin_here && jj == 1 && ii == 2) pl = 0.0; // (never true: ii is odd) kept for clarity of the pin rule
         }
-        if (jj <= g.ny) {
-            double gradp = fin0((pc - pl) * g.idx);
-            u[o] = sanitize_val(u[o] - dt * gradp, flag);
+        if (active) {
+            if (jj <= g.ny) { // u faces ii, ii+1 of row jj (project.cpp:51-65)
+                double2 uu = *reinterpret_cast<const double2 *>(u + o);
+                double ga = fin0((pc.x - pl) * g.idx);
+                double gb = fin0((pc.y - pc.x) * g.idx);
+                uu.x = sanitize_val(uu.x - dt * ga, flag);
+                if (u_b) {
+                    uu.y = sanitize_val(uu.y - dt * gb, flag);
+                    *reinterpret_cast<double2 *>(u + o) = uu;
+                } else {
+                    u[o] = uu.x;
+                }
+            }
+            if (v_a) { // v faces of row jj (project.cpp:69-83); rows up to ny+1 on the top slab
+                double2 vv = *reinterpret_cast<const double2 *>(v + o);
+                double ga = fin0((pc.x - pb.x) * g.idy);
+                double gb = fin0((pc.y - pb.y) * g.idy);
+                vv.x = sanitize_val(vv.x - dt * ga, flag);
+                if (v_b) {
+                    vv.y = sanitize_val(vv.y - dt * gb, flag);
+                    *reinterpret_cast<double2 *>(v + o) = vv;
+                } else {
+                    v[o] = vv.x;
+                }
+            }
+            if (pin_here && jj == 1 && ii == 1) p[o] = 0.0;
         }
-        if (ii <= g.nx) {
-            double gradp = fin0((pc - pb) * g.idy);
-            v[o] = sanitize_val(v[o] - dt * gradp, flag);
-        }
-        if (pin_here && jj == 1 && ii == 1) p[o] = 0.0;
+        pb = pc;
     }
     if (flag) flags->nonfinite_any = 1;
 }
