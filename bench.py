@@ -171,24 +171,43 @@ def main():
         return
 
     import torch
+    import torch.distributed as dist
     if world != N:
         raise SystemExit(f"--gpus {N} needs {N} ranks (torchrun --nproc-per-node {N}); WORLD_SIZE={world}")
-    if N > 1:
-        raise SystemExit("row-slab multi-GPU path not available in this build")
     torch.cuda.set_device(local_rank)
     cfd = importlib.import_module("macos-cfd_b200")
+    comm = None
+    if N > 1:  # one process per GPU; torch.distributed (NCCL) is the plumbing: id broadcast, barriers, max over ranks
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        ids = [cfd.comm_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        comm = ids[0]
     bc, Re, CFL = cfd.preset(preset, Ly)
     pp = cfd.make_params(solver, vcycles=vcycles, tol=tol, pcg_max_iters=iters)
-    s = cfd.Solver(nx, ny, Lx, Ly, device=local_rank)
+    s = cfd.Solver(nx, ny, Lx, Ly, device=local_rank, rank=rank, nranks=N, comm_id=comm)
     s.set_variant(args.variant)
     sh = s.shapes()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if N > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if N == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
     stream = torch.cuda.ExternalStream(s.stream, device=local_rank)
     flush = None if nx * ny_gpu * 8 > 200e6 else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     cells = nx * ny
 
     import numpy as np
     zero = {k: np.zeros(v) for k, v in sh.items()}
-    u_init = cfd.shear_initial_u(nx, ny, Ly) if preset == "shear" else zero["u"]
+    u_init = (np.ascontiguousarray(cfd.shear_initial_u(nx, ny, Ly)[s.row0:s.row0 + s.nrows + 2]) if preset == "shear"
+              else zero["u"])
 
     def reset():
         """GUI-style reset (main.cpp:338-358): all fields and work arrays back to the deterministic initial state.
@@ -207,7 +226,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = s.launch_count
-    torch.cuda.synchronize()
+    barrier()
     if flush is None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -215,8 +234,8 @@ def main():
             s.step_async(bc, Re, CFL, pp)
         e1.record(stream)
         info = s.sync()
-        torch.cuda.synchronize()
-        total_ms = e0.elapsed_time(e1)
+        barrier()
+        total_ms = max_over_ranks(e0.elapsed_time(e1))
     else:
         total_ms = 0.0
         for _ in range(args.steps):
@@ -227,7 +246,8 @@ def main():
             s.step_async(bc, Re, CFL, pp)
             e1.record(stream)
             info = s.sync()
-            total_ms += e0.elapsed_time(e1)
+            barrier()
+            total_ms += max_over_ranks(e0.elapsed_time(e1))
     launches = s.launch_count - l0
     clocks = sampler.stop()
     ms_per_step = total_ms / args.steps
@@ -249,12 +269,13 @@ def main():
     peak, peak_src = measured_peaks()
     stage_bytes = dict(STAGE_BYTES, pressure_solve=solve_bytes(solver, vcycles, info.iters))
     stages = {}
+    cells_rank = nx * s.nrows  # stage times are this rank's: its kernels move this rank's cells
     for k, ms in acc.items():
-        b = stage_bytes.get(k, 0) * cells
+        b = stage_bytes.get(k, 0) * cells_rank
         stages[k] = {"ms": round(ms, 4), "gbs": round(b / (ms * 1e-3) / 1e9, 1) if ms > 0 and b else None}
     top = max((k for k in acc if stage_bytes.get(k)), key=lambda k: acc[k])
-    achieved = stage_bytes[top] * cells / (acc[top] * 1e-3) / 1e9
-    step_bytes = sum(stage_bytes.values()) * cells
+    achieved = stage_bytes[top] * cells_rank / (acc[top] * 1e-3) / 1e9
+    step_bytes = sum(stage_bytes.values()) * cells_rank
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "bytes_per_cell": stage_bytes[top],
@@ -275,17 +296,17 @@ def main():
         ke = max(2, min(args.steps, 4))
         for _ in range(1):
             s.upload(hu, hv, hp); s.step(bc, Re, CFL, pp); s.download(hu, hv, hp, hr)
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(ke):
             s.upload(hu, hv, hp)
             s.step(bc, Re, CFL, pp)
             s.download(hu, hv, hp, hr)
         torch.cuda.synchronize()
-        t = time.perf_counter() - t0
+        t = max_over_ranks(time.perf_counter() - t0)
         h2d = (hu.numel() + hv.numel() + hp.numel()) * 8
         d2h = h2d + hr.numel() * 8
-        e2e = {"value": cells * ke / t, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        e2e = {"value": cells * ke / t, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d * N, "d2h_bytes_per_step": d2h * N,
                "steps": ke, "ms_per_step": 1e3 * t / ke,
                "path": "cfd_b200_upload -> cfd_b200_step -> cfd_b200_download (pinned host State)"}
         del hu, hv, hp, hr
@@ -293,7 +314,12 @@ def main():
     line = dict(base, value=value, ms_per_step=ms_per_step, clocks=clocks, e2e=e2e, gpu_launches=launches,
                 roofline=roofline, last_step={"dt": info.dt, "residual": info.residual, "iters": info.iters})
     s.close()
-    if not args.no_cpu_baseline:
+    if N > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    if not args.no_cpu_baseline and N == 1:
         r = cpu_reference_run(wl, 2, 1, 4096 if solver == "mg" else 1024)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))

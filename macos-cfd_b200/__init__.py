@@ -163,14 +163,40 @@ def _addr(a):
     return a.data_ptr()  # torch tensor (pinned host memory in bench.py)
 
 
+def comm_id() -> bytes:
+    """A fresh 128-byte NCCL unique id (call on rank 0, hand the bytes to every rank's Solver)."""
+    L = load_library()
+    buf = C.create_string_buffer(128)
+    rc = L.cfd_b200_comm_id(buf)
+    if rc != 0:
+        raise CfdError(rc, L.cfd_b200_last_error().decode())
+    return buf.raw
+
+
+def slab_rows(ny: int, rank: int, nranks: int):
+    """(row0, nrows) of rank's slab -- the same partition the library uses (csrc/comm.cuh slab_partition)."""
+    a, b = ny * rank // nranks, ny * (rank + 1) // nranks
+    return a, b - a
+
+
 class Solver:
     """Grid + device State + PressureSolver + TimeIntegrator of the reference (main.cpp:104-130) on one B200."""
 
-    def __init__(self, nx, ny, Lx=1.0, Ly=1.0, device=0):
+    def __init__(self, nx, ny, Lx=1.0, Ly=1.0, device=0, rank=0, nranks=1, comm_id: bytes | None = None):
+        """Single GPU by default.  With nranks > 1 this is one row slab of the nx x ny grid (one process per GPU);
+        comm_id is the 128-byte id from ``comm_id()`` on rank 0, distributed by the caller."""
         self.L = load_library()
         self.nx, self.ny, self.Lx, self.Ly = nx, ny, Lx, Ly
+        self.rank, self.nranks = rank, nranks
         self.h = C.c_void_p()
-        self._check(self.L.cfd_b200_create(nx, ny, Lx, Ly, device, C.byref(self.h)))
+        if nranks == 1:
+            self._check(self.L.cfd_b200_create(nx, ny, Lx, Ly, device, C.byref(self.h)))
+        else:
+            buf = C.create_string_buffer(comm_id, 128)
+            self._check(self.L.cfd_b200_create_slab(nx, ny, Lx, Ly, device, rank, nranks, buf, C.byref(self.h)))
+        r0, nr = C.c_int(), C.c_int()
+        self._check(self.L.cfd_b200_slab_rows(self.h, C.byref(r0), C.byref(nr)))
+        self.row0, self.nrows = r0.value, nr.value  # owned cell rows [row0, row0 + nrows)
 
     def _check(self, rc):
         if rc != 0:
@@ -178,7 +204,9 @@ class Solver:
 
     # reference host layout
     def shapes(self):
-        return {"u": (self.ny + 2, self.nx + 3), "v": (self.ny + 3, self.nx + 2), "p": (self.ny + 2, self.nx + 2)}
+        """Host arrays of THIS handle: the whole grid, or the slab's rows plus one ghost/halo row on either side."""
+        n = self.nrows
+        return {"u": (n + 2, self.nx + 3), "v": (n + 3, self.nx + 2), "p": (n + 2, self.nx + 2)}
 
     def upload(self, u=None, v=None, p=None, rhs=None):
         self._check(self.L.cfd_b200_upload(self.h, _addr(u), _addr(v), _addr(p)))

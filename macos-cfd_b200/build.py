@@ -36,7 +36,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: libcfd_b200.so cannot be built (there is no CPU fallback)")
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "capi.cu")]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "capi.cu"), "-ldl"]
     env = dict(os.environ)
     env.pop("CC", None), env.pop("CXX", None)  # the image's /opt/gcc wrappers are not meant for nvcc's host pass
     r = subprocess.run(cmd, capture_output=True, text=True, env=env)

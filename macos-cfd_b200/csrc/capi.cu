@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 
+#include "comm.cuh"
 #include "common.cuh"
 #include "kernels_pressure.cuh"
 #include "kernels_step.cuh"
@@ -65,6 +66,7 @@ struct cfd_b200_solver {
     cudaEvent_t ev[ST_COUNT] = {};
     bool ev_valid = false;
     int sm_count = 148;
+    ncclComm_t comm = nullptr; // row slabs only
 };
 
 namespace {
@@ -149,7 +151,8 @@ void enqueue_cfl(cfd_b200_solver *s, double Re, double CFL, double dt_override, 
         LAUNCH(s, k_absmax, grid, 256, g, s->u, s->v, s->d_sc);
     }
     s->cfl_cached = false;
-    // (slabs: max-allreduce of umax/vmax goes here)
+    // non-negative doubles order like their bit patterns, so the maxima can be all-reduced as doubles
+    if (s->nranks > 1) nccl_api().AllReduce(&s->d_sc->umax_bits, &s->d_sc->umax_bits, 2, ncclDouble, ncclMax, s->comm, s->stream);
     LAUNCH(s, k_dt, 1, 1, g, Re, CFL, dt_override, s->d_sc, cfl_only);
 }
 
@@ -209,22 +212,98 @@ int pcg_grid(const cfd_b200_solver *s, int ntiles) {
     return ntiles < cap ? ntiles : cap;
 }
 
+// ---- row-slab communication (no-ops on a single-GPU handle) -----------------------------------------------------
+enum { HALO_UP = 1, HALO_DOWN = 2, HALO_BOTH = 3 }; // direction in which OWNED rows are sent
+
+#define NCCLCHK(call)                                                                                           \
+    do {                                                                                                        \
+        ncclResult_t r_ = (call);                                                                               \
+        if (r_ != ncclSuccess) return fail(CFD_B200_ECOMM, "%s:%d %s: %s", __FILE__, __LINE__, #call,           \
+                                           nccl_api().GetErrorString(r_));                                      \
+    } while (0)
+
+// Send the top `rows` owned rows of each field to the slab above (HALO_UP) and/or the bottom `rows` owned rows to the
+// slab below (HALO_DOWN); receive the neighbours' rows into the halo rows.  Rows are contiguous: one message each.
+int halo_exchange(cfd_b200_solver *s, double *const *fields, int nfields, int rows, int dirs) {
+    if (s->nranks == 1) return 0;
+    const Geom &g = s->g;
+    NcclApi &n = nccl_api();
+    const size_t cnt = (size_t)rows * g.P;
+    auto rowptr = [&](double *f, int jj) { return f + (size_t)(jj + CFD_YOFF) * g.P; };
+    NCCLCHK(n.GroupStart());
+    for (int k = 0; k < nfields; ++k) {
+        double *f = fields[k];
+        if (!g.top) { // neighbour above = rank + 1
+            if (dirs & HALO_UP) NCCLCHK(n.Send(rowptr(f, g.ny - rows + 1), cnt, ncclDouble, s->rank + 1, s->comm, s->stream));
+            if (dirs & HALO_DOWN) NCCLCHK(n.Recv(rowptr(f, g.ny + 1), cnt, ncclDouble, s->rank + 1, s->comm, s->stream));
+        }
+        if (!g.bottom) { // neighbour below = rank - 1
+            if (dirs & HALO_DOWN) NCCLCHK(n.Send(rowptr(f, 1), cnt, ncclDouble, s->rank - 1, s->comm, s->stream));
+            if (dirs & HALO_UP) NCCLCHK(n.Recv(rowptr(f, 1 - rows), cnt, ncclDouble, s->rank - 1, s->comm, s->stream));
+        }
+    }
+    NCCLCHK(n.GroupEnd());
+    return 0;
+}
+int halo_exchange2(cfd_b200_solver *s, double *a, double *b, int rows, int dirs) {
+    double *f[2] = {a, b};
+    return halo_exchange(s, f, b ? 2 : 1, rows, dirs);
+}
+// in-place allreduce of `count` doubles in device memory (PCG dots, residual, CFL maxima, divergence sums)
+int allreduce(cfd_b200_solver *s, void *dev, int count, ncclRedOp_t op) {
+    if (s->nranks == 1) return 0;
+    NCCLCHK(nccl_api().AllReduce(dev, dev, (size_t)count, ncclDouble, op, s->comm, s->stream));
+    return 0;
+}
+#define TRY(call)                                                                                               \
+    do {                                                                                                        \
+        int rc_ = (call);                                                                                       \
+        if (rc_) return rc_;                                                                                    \
+    } while (0)
+
+template <int POW2>
+void launch_fused(cfd_b200_solver *s, double tol, int ntx, int nty, int finish) {
+    const Geom &g = s->g;
+    if ((1 + g.j0) & 1)
+        k_rbgs_fused<POW2, 1><<<ntx * nty, RB_THREADS, RB_SMEM, s->stream>>>(g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, ntx, finish);
+    else
+        k_rbgs_fused<POW2, 0><<<ntx * nty, RB_THREADS, RB_SMEM, s->stream>>>(g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, ntx, finish);
+    s->launches++;
+}
+
 // PressureSolver::solve, pressure.cpp:113-242.  The whole solve is enqueued; convergence is tested on the device.
+// Row slabs: every grid-level sum is completed by an allreduce + a one-thread tail kernel (identical on all ranks),
+// and the rows a neighbour's stencil reads are exchanged where the single-GPU path would simply read them.
 int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
     const Geom &g = s->g;
+    const int single = s->nranks == 1;
     if (pp->solver == CFD_B200_SOLVER_PCG) {
         cudaMemsetAsync(s->p, 0, s->n * sizeof(double), s->stream); // pressure.cpp:133-134
         {
             dim3 grid(cdiv(g.nx, 512), g.ny < 256 ? g.ny : 256);
-            LAUNCH(s, k_pcg_init, grid, PT_THREADS, g, s->rhs, s->r, s->d_sc, s->partials, pp->tol, pp->pcg_max_iters, 1);
+            LAUNCH(s, k_pcg_init, grid, PT_THREADS, g, s->rhs, s->r, s->d_sc, s->partials, pp->tol, pp->pcg_max_iters, single);
+        }
+        if (!single) {
+            TRY(allreduce(s, s->d_sc->red, 2, ncclSum));
+            LAUNCH(s, k_pcg_fin_init, 1, 1, s->d_sc, pp->tol, pp->pcg_max_iters);
+            TRY(halo_exchange2(s, s->r, nullptr, 1, HALO_BOTH));
         }
         const int ntx = cdiv(g.nx, PT_X), nty = cdiv(g.ny, PT_Y), ntiles = ntx * nty;
         const int grid = pcg_grid(s, ntiles);
         double *s_old = s->sA, *s_new = s->sB;
         for (int it = 0; it < pp->pcg_max_iters; ++it) {
-            LAUNCH(s, k_pcg_phase1, grid, PT_THREADS, g, s->r, s_old, s_new, s->d_sc, s->partials, ntx, ntiles, 1);
+            LAUNCH(s, k_pcg_phase1, grid, PT_THREADS, g, s->r, s_old, s_new, s->d_sc, s->partials, ntx, ntiles, single);
+            if (!single) {
+                TRY(allreduce(s, s->d_sc->red, 1, ncclSum));
+                LAUNCH(s, k_pcg_fin1, 1, 1, s->d_sc);
+            }
             LAUNCH(s, k_pcg_phase2, grid, PT_THREADS, g, s->p, s->r, s_new, s->d_sc, s->partials, ntx, ntiles, pp->tol,
-                   pp->pcg_max_iters, 1);
+                   pp->pcg_max_iters, single);
+            if (!single) {
+                TRY(allreduce(s, s->d_sc->red, 2, ncclSum));
+                LAUNCH(s, k_pcg_fin2, 1, 1, s->d_sc, pp->tol, pp->pcg_max_iters);
+                TRY(halo_exchange2(s, s->r, nullptr, 1, HALO_BOTH)); // the next direction update reads r one row out
+            }
             double *t = s_old;
             s_old = s_new;
             s_new = t;
@@ -233,14 +312,17 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
         if (pp->mg_mode != CFD_B200_MG_REFERENCE)
             return fail(CFD_B200_EUNSUPPORTED, "mg_mode=VCYCLE is not implemented yet");
         LAUNCH(s, k_solve_begin, 1, 1, s->d_sc);
-        if (s->variant != 0 && s->nranks == 1) { // fused smooth(): 4 colour passes + residual per launch, p ping-ponged
+        if (s->variant != 0) { // fused smooth(): 4 colour passes + residual per launch, p ping-ponged
             const int ntx = cdiv(g.nx, RB_TX), nty = cdiv(g.ny, RB_TY);
+            if (!single) TRY(halo_exchange2(s, s->rhs, nullptr, RB_HY, HALO_BOTH)); // rhs is constant during the solve
             for (int vc = 0; vc < pp->vcycles; ++vc) {
-                if (g.denom_pow2)
-                    k_rbgs_fused<1, 1><<<ntx * nty, RB_THREADS, RB_SMEM, s->stream>>>(g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, pp->tol, ntx);
-                else
-                    k_rbgs_fused<0, 1><<<ntx * nty, RB_THREADS, RB_SMEM, s->stream>>>(g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, pp->tol, ntx);
-                s->launches++;
+                if (!single) TRY(halo_exchange2(s, s->p, nullptr, RB_HY, HALO_BOTH)); // 5 rows: redundant compute
+                if (g.denom_pow2) launch_fused<1>(s, pp->tol, ntx, nty, single);
+                else launch_fused<0>(s, pp->tol, ntx, nty, single);
+                if (!single) {
+                    TRY(allreduce(s, s->d_sc->red, 1, ncclSum));
+                    LAUNCH(s, k_rbgs_fin, 1, 1, s->d_sc, pp->tol);
+                }
                 double *t = s->p;
                 s->p = s->p_alt;
                 s->p_alt = t;
@@ -253,12 +335,18 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
         for (int vc = 0; vc < pp->vcycles; ++vc) {
             for (int sweep = 0; sweep < 2; ++sweep) // the literal 2 of pressure.cpp:119
                 for (int colour = 0; colour < 2; ++colour) {
+                    if (!single) TRY(halo_exchange2(s, s->p, nullptr, 1, HALO_BOTH));
                     if (g.denom_pow2)
                         LAUNCH(s, k_rbgs_colour<1>, cgrid, cblock, g, s->p, s->rhs, colour, s->d_sc);
                     else
                         LAUNCH(s, k_rbgs_colour<0>, cgrid, cblock, g, s->p, s->rhs, colour, s->d_sc);
                 }
-            LAUNCH(s, k_rbgs_residual, rgrid, 256, g, s->p, s->rhs, s->d_sc, s->partials, pp->tol, 1);
+            if (!single) TRY(halo_exchange2(s, s->p, nullptr, 1, HALO_BOTH));
+            LAUNCH(s, k_rbgs_residual, rgrid, 256, g, s->p, s->rhs, s->d_sc, s->partials, pp->tol, single);
+            if (!single) {
+                TRY(allreduce(s, s->d_sc->red, 1, ncclSum));
+                LAUNCH(s, k_rbgs_fin, 1, 1, s->d_sc, pp->tol);
+            }
         }
     }
     LAUNCH(s, k_solve_finish, 1, 1, s->d_sc);
@@ -285,28 +373,34 @@ int enqueue_step(cfd_b200_solver *s, const cfd_b200_bc *bc_in, double Re, double
     s->last_bc = *bc_in;
     stage_mark(s, ST_BC0);
     enqueue_bc(s, bc, s->u, s->v, s->p, 0); // :51-53
+    TRY(halo_exchange2(s, s->u, s->v, 2, HALO_BOTH)); // the advection stencil reads 2 rows beyond the slab
     stage_mark(s, ST_CFL);
     enqueue_cfl(s, Re, CFL, dt_override, 0); // :55-66
     stage_mark(s, ST_RHS1);
     enqueue_rhs<1>(s, invRe, s->u, s->v, s->u1, s->v1); // :71-103
     stage_mark(s, ST_BC1);
     enqueue_bc(s, bc, s->u1, s->v1, nullptr, 1); // :106-107
+    TRY(halo_exchange2(s, s->u1, s->v1, 2, HALO_BOTH));
     stage_mark(s, ST_RHS2);
     enqueue_rhs<2>(s, invRe, s->u1, s->v1, s->u, s->v); // :109-147
     stage_mark(s, ST_BC2);
     enqueue_bc(s, bc, s->u, s->v, nullptr, 1); // :150-155
+    TRY(halo_exchange2(s, s->v, nullptr, 1, HALO_DOWN)); // divergence of the top cell row reads the v face above it
     stage_mark(s, ST_DIV);
     enqueue_divergence(s, 1, 1); // :158-186
     stage_mark(s, ST_SOLVE);
     int rc = enqueue_solve(s, pp); // :187
     if (rc) return rc;
+    TRY(halo_exchange2(s, s->p, nullptr, 1, HALO_UP)); // v faces of the bottom row read p one row below the slab
     stage_mark(s, ST_PROJECT);
     enqueue_project(s, s->d_sc, 0.0); // :188-202
     stage_mark(s, ST_BC3);
     enqueue_bc(s, bc, s->u, s->v, s->p, 1); // :205-207
+    TRY(halo_exchange2(s, s->v, nullptr, 1, HALO_DOWN));
     stage_mark(s, ST_DIV2);
     enqueue_divergence(s, 0, 1, 1); // :210-220 (+ max|u|, max|v| for the next step's compute_cfl)
     s->cfl_cached = true;
+    TRY(allreduce(s, &s->d_sc->div_before, 2, ncclSum)); // slabs hold partial sums of squares here
     LAUNCH(s, k_sanitize_if, s->sm_count * 4, 256, g, s->p, s->d_sc); // :236
     stage_mark(s, ST_END);
     s->ev_valid = s->profiling != 0;
@@ -324,6 +418,11 @@ void fill_info(const cfd_b200_solver *s, cfd_b200_step_info *info) {
     info->pcg_breakdown = h.breakdown_iter;
     info->div_before = h.div_before;
     info->div_after = h.div_after;
+    if (s->nranks > 1) { // the kernels left global sums of squares (time_integrator.cpp:171, :220 finish them)
+        const double ncell = (double)(s->g.nx * s->g.ny_glob);
+        info->div_before = std::sqrt(h.div_before / ncell);
+        info->div_after = std::sqrt(h.div_after / ncell);
+    }
     info->nonfinite = (h.nonfinite_any ? 1 : 0) | (h.nonfinite_res ? 2 : 0);
 }
 
@@ -364,14 +463,26 @@ int cfd_b200_device_count(void) {
     return n;
 }
 
-int cfd_b200_comm_id(void *) { return fail(CFD_B200_EUNSUPPORTED, "multi-GPU slabs are not built into this library yet"); }
+int cfd_b200_comm_id(void *id128) {
+    if (!id128) return fail(CFD_B200_EINVAL, "id128 is NULL");
+    NcclApi &n = nccl_api();
+    if (!n.load()) return fail(CFD_B200_ECOMM, "NCCL unavailable: %s", n.error);
+    ncclUniqueId id;
+    ncclResult_t r = n.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(CFD_B200_ECOMM, "ncclGetUniqueId: %s", n.GetErrorString(r));
+    memcpy(id128, &id, sizeof(id));
+    return 0;
+}
 
-int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int rank, int nranks, const void *,
+int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int rank, int nranks, const void *nccl_id128,
                          cfd_b200_solver **out) {
     if (!out) return fail(CFD_B200_EINVAL, "out is NULL");
     *out = nullptr;
     if (nx < 4 || ny < 4 || !(Lx > 0.0) || !(Ly > 0.0)) return fail(CFD_B200_EINVAL, "need nx, ny >= 4 and Lx, Ly > 0");
-    if (nranks != 1 || rank != 0) return fail(CFD_B200_EUNSUPPORTED, "multi-GPU slabs are not built into this library yet");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(CFD_B200_EINVAL, "bad rank %d of %d", rank, nranks);
+    if (nranks > 1 && !nccl_id128) return fail(CFD_B200_EINVAL, "nccl_id128 is NULL");
+    if (nranks > 1 && ny / nranks < 8) return fail(CFD_B200_EINVAL, "need at least 8 cell rows per slab");
+    if (nranks > 1 && !nccl_api().load()) return fail(CFD_B200_ECOMM, "NCCL unavailable: %s", nccl_api().error);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev <= 0)
@@ -384,7 +495,9 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
     s->device = device;
     s->rank = rank;
     s->nranks = nranks;
-    fill_geom(s->g, nx, ny, Lx, Ly, 0, ny, 1, 1);
+    int row0 = 0, nrows = ny;
+    slab_partition(ny, rank, nranks, &row0, &nrows);
+    fill_geom(s->g, nx, ny, Lx, Ly, row0, nrows, rank == 0, rank == nranks - 1);
     s->n = (size_t)s->g.P * s->g.rows;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->sm_count = prop.multiProcessorCount;
@@ -401,11 +514,13 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
         memset(s->h_sc, 0, sizeof(Scalars));
         s->partials_n = 2 * 65536;
         {
-            size_t tiles = (size_t)cdiv(nx, RB_TX) * cdiv(ny, RB_TY);
+            size_t tiles = (size_t)cdiv(nx, RB_TX) * cdiv(nrows, RB_TY);
             if (2 * tiles > s->partials_n) s->partials_n = 2 * tiles;
         }
         if (cudaFuncSetAttribute(k_rbgs_fused<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM) != cudaSuccess ||
-            cudaFuncSetAttribute(k_rbgs_fused<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM) != cudaSuccess) {
+            cudaFuncSetAttribute(k_rbgs_fused<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(k_rbgs_fused<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(k_rbgs_fused<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM) != cudaSuccess) {
             rc = fail(CFD_B200_ECUDA, "cudaFuncSetAttribute(k_rbgs_fused) failed: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }
@@ -414,6 +529,12 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
             if (cudaEventCreate(&s->ev[i]) != cudaSuccess) { rc = fail(CFD_B200_ECUDA, "event create failed"); break; }
         if (rc) break;
         if (cudaStreamSynchronize(s->stream) != cudaSuccess) { rc = fail(CFD_B200_ECUDA, "init sync failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        if (nranks > 1) { // collective: every rank of the job must be here
+            ncclUniqueId id;
+            memcpy(&id, nccl_id128, sizeof(id));
+            ncclResult_t r = nccl_api().CommInitRank(&s->comm, nranks, id, rank);
+            if (r != ncclSuccess) { rc = fail(CFD_B200_ECOMM, "ncclCommInitRank: %s", nccl_api().GetErrorString(r)); break; }
+        }
     } while (0);
     if (rc) {
         cfd_b200_destroy(s);
@@ -438,6 +559,7 @@ void cfd_b200_destroy(cfd_b200_solver *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->comm) nccl_api().CommDestroy(s->comm);
     double *fields[] = {s->u, s->v, s->p, s->p_alt, s->rhs, s->u1, s->v1, s->r, s->sA, s->sB, s->scratch_u, s->scratch_v, s->partials};
     for (double *f : fields)
         if (f) cudaFree(f);
@@ -532,7 +654,16 @@ int cfd_b200_divergence_l2(cfd_b200_solver *s, double *out) {
     const Geom &g = s->g;
     CU(cudaMemsetAsync(&s->d_sc->diag_max_bits, 0, sizeof(unsigned long long), s->stream));
     dim3 grid(cdiv(g.nx, 256), g.ny < 128 ? g.ny : 128);
+    if (s->nranks > 1) { // the top cell row reads the v face owned by the slab above
+        int rc = halo_exchange2(s, s->v, nullptr, 1, HALO_DOWN);
+        if (rc) return rc;
+    }
     LAUNCH(s, k_diag, grid, 256, g, s->u, s->v, s->d_sc, s->partials);
+    if (s->nranks > 1) {
+        int rc = allreduce(s, &s->d_sc->diag_sum, 1, ncclSum);
+        if (!rc) rc = allreduce(s, &s->d_sc->diag_max_bits, 1, ncclMax);
+        if (rc) return rc;
+    }
     CU(cudaMemcpyAsync(s->h_sc, s->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     double denom = static_cast<double>(g.nx) * g.ny_glob; // metrics.cpp:84

@@ -11,12 +11,13 @@
 // serves all of them: raw reference index (ii, jj) [ii = i + ngx, jj = j + ngy, ng = 1; field.hpp:69] lives at
 //     element (jj + YOFF) * P + (ii + XOFF)
 // XOFF = 15 puts raw column 1 (the first interior cell / face) on a 128-byte boundary, so a warp that starts
-// at an even interior column issues aligned 16-byte (double2) accesses.  YOFF = 2 and >= 2 columns of right
-// padding let stencil kernels read +-2 without bounds checks inside the allocation.  The pitch P is a
+// at an even interior column issues aligned 16-byte (double2) accesses.  YOFF = 6 rows below and above hold the
+// halo rows of a row slab (2 for the advection stencil, 5 for the temporally blocked smoother) and, like the >= 2
+// columns of right padding, let stencil kernels read +-2 without bounds checks inside the allocation.  The pitch P is a
 // multiple of 16 doubles (128 B).  Padding is zero-filled once and never written.
 // ---------------------------------------------------------------------------------------------------------
 #define CFD_XOFF 15
-#define CFD_YOFF 2
+#define CFD_YOFF 6
 
 struct Geom {
     int nx;       // cells per row
@@ -70,6 +71,7 @@ struct Scalars {
     double diag_sum;     // divergence_l2 accumulator
     unsigned long long diag_max_bits;
     unsigned int ticket[4]; // last-block tickets of the grid reductions
+    double red[4];          // row slabs: local partial sums handed to the allreduce, then to the k_*_fin kernels
 };
 
 // ---------------------------------------------------------------------------------------------------------

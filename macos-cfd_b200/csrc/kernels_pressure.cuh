@@ -37,6 +37,56 @@ __device__ __forceinline__ bool s_live(const Geom &g, int ii, int jj) {
     return ii >= 1 && ii <= g.nx && jj >= (g.bottom ? 1 : 0) && jj <= (g.top ? g.ny : g.ny + 1);
 }
 
+// ---- scalar tails of the solver (thread 0 of the last block on one GPU; a one-thread kernel after the allreduce on
+//      row slabs, where every rank evaluates them on the same reduced numbers) ----------------------------------
+// after PCG start: rho = dot(r,z), res = sqrt(max(0, dot(r,r))), loop condition (pressure.cpp:175-179)
+__device__ __forceinline__ void pcg_tail_init(Scalars *sc, double rz, double rr, double tol, int max_iters) {
+    sc->rho = rz;
+    sc->first = 1;
+    sc->iters = 0;
+    sc->breakdown_iter = -1;
+    double res = sqrt(max2(0.0, rr));
+    sc->res = res;
+    sc->done = !(max_iters > 0 && res > tol);
+}
+// after dot(s, Ap): breakdown test and alpha (pressure.cpp:182-187)
+__device__ __forceinline__ void pcg_tail1(Scalars *sc, double denom) {
+    if (!finite_d(denom) || fabs(denom) < 1e-20) {
+        sc->breakdown_iter = sc->iters;
+        sc->done = 1;
+    } else {
+        sc->alpha = sc->rho / denom;
+    }
+}
+// after the p/r update: residual test (:202-204), rho_new / beta (:216-219, :229), loop condition (:179)
+__device__ __forceinline__ void pcg_tail2(Scalars *sc, double rr, double rz, double tol, int max_iters) {
+    double res = sqrt(max2(0.0, rr));
+    sc->res = res;
+    sc->first = 0;
+    int it = sc->iters + 1;
+    sc->iters = it;
+    if (!finite_d(res) || res < tol) {
+        sc->done = 1;
+    } else if (!finite_d(rz)) {
+        sc->done = 1;
+    } else {
+        sc->beta = rz / sc->rho;
+        sc->rho = rz;
+        if (!(it < max_iters && res > tol)) sc->done = 1;
+    }
+}
+// after smooth(): res = sqrt(dot(r,r)) and the vcycle loop exit (pressure.cpp:110, :118-122)
+__device__ __forceinline__ void rbgs_tail(Scalars *sc, double rr, double tol) {
+    double res = sqrt(rr);
+    sc->res = res;
+    sc->iters = sc->iters + 1;
+    if (res < tol) sc->done = 1;
+}
+__global__ void k_pcg_fin_init(Scalars *sc, double tol, int max_iters) { pcg_tail_init(sc, sc->red[0], sc->red[1], tol, max_iters); }
+__global__ void k_pcg_fin1(Scalars *sc) { if (!sc->done) pcg_tail1(sc, sc->red[0]); }
+__global__ void k_pcg_fin2(Scalars *sc, double tol, int max_iters) { if (!sc->done) pcg_tail2(sc, sc->red[0], sc->red[1], tol, max_iters); }
+__global__ void k_rbgs_fin(Scalars *sc, double tol) { if (!sc->done) rbgs_tail(sc, sc->red[0], tol); }
+
 // PCG start (pressure.cpp:133-177): p = 0 everywhere (done by a memset before this kernel), Ap = L(0) = 0,
 // r = fin0(rhs) - 0, rho = dot(r, inv_diag*r), res = sqrt(max(0, dot(r,r))).  z and s are not stored: the
 // first direction update recomputes z = inv_diag*r (flag `first`).
@@ -66,16 +116,8 @@ __global__ void __launch_bounds__(PT_THREADS)
         }
     }
     grid_sum<2>(acc, partials, &sc->ticket[2], [=](double(&t)[2]) {
-        sc->rho = t[0];
-        sc->denom = t[1]; // rr, kept for the multi-GPU finish
-        sc->first = 1;
-        sc->iters = 0;
-        sc->breakdown_iter = -1;
-        if (finish) {
-            double res = sqrt(max2(0.0, t[1]));
-            sc->res = res;
-            sc->done = !(max_iters > 0 && res > tol); // loop condition, pressure.cpp:179
-        }
+        if (finish) pcg_tail_init(sc, t[0], t[1], tol, max_iters);
+        else { sc->red[0] = t[0]; sc->red[1] = t[1]; }
     });
 }
 
@@ -154,16 +196,8 @@ __global__ void __launch_bounds__(PT_THREADS)
         __syncthreads();
     }
     grid_sum<1>(acc, partials, &sc->ticket[2], [=](double(&t)[1]) {
-        sc->denom = t[0];
-        if (finish) {
-            double denom = t[0];
-            if (!finite_d(denom) || fabs(denom) < 1e-20) { // "PCG breakdown", pressure.cpp:183-186
-                sc->breakdown_iter = sc->iters;
-                sc->done = 1;
-            } else {
-                sc->alpha = sc->rho / denom;
-            }
-        }
+        if (finish) pcg_tail1(sc, t[0]);
+        else sc->red[0] = t[0];
     });
 }
 
@@ -239,28 +273,8 @@ __global__ void __launch_bounds__(PT_THREADS)
     }
     if (pflag) sc->nonfinite_p = 1;
     grid_sum<2>(acc, partials, &sc->ticket[2], [=](double(&t)[2]) {
-        if (!finish) { // multi-GPU: raw sums, finished after the allreduce
-            sc->denom = t[0];
-            sc->alpha = t[1];
-        } else {
-            double res = sqrt(max2(0.0, t[0]));
-            sc->res = res;
-            sc->first = 0;
-            int it = sc->iters + 1;
-            sc->iters = it;
-            if (!finite_d(res) || res < tol) { // pressure.cpp:203
-                sc->done = 1;
-            } else {
-                double rho_new = t[1];
-                if (!finite_d(rho_new)) { // :217
-                    sc->done = 1;
-                } else {
-                    sc->beta = rho_new / sc->rho;
-                    sc->rho = rho_new;
-                    if (!(it < max_iters && res > tol)) sc->done = 1; // loop condition, :179
-                }
-            }
-        }
+        if (finish) pcg_tail2(sc, t[0], t[1], tol, max_iters);
+        else { sc->red[0] = t[0]; sc->red[1] = t[1]; }
     });
 }
 
@@ -318,13 +332,8 @@ __global__ void __launch_bounds__(256)
     }
     if (pflag) sc->nonfinite_p = 1;
     grid_sum<1>(acc, partials, &sc->ticket[2], [=](double(&t)[1]) {
-        sc->denom = t[0];
-        if (finish) {
-            double res = sqrt(t[0]);
-            sc->res = res;
-            sc->iters = sc->iters + 1;
-            if (res < tol) sc->done = 1;
-        }
+        if (finish) rbgs_tail(sc, t[0], tol);
+        else sc->red[0] = t[0];
     });
 }
 

@@ -14,7 +14,7 @@
 // (the reference guards every neighbour read with isfinite, pressure.cpp:84-88); the unsanitised value goes to
 // global memory at a point's last update.
 #pragma once
-#include "common.cuh"
+#include "kernels_pressure.cuh"
 
 // Tile geometry.  A thread owns RB_M x RB_N slots (a slot = aligned pair of columns): rows ly = RB_M*warp + m,
 // column pairs k = lane + 32 n.  Default: 128 x 64 tile, 512 threads (2 blocks/SM); -DRB_N=1: 64 x 64 tile, 256 threads.
@@ -65,7 +65,7 @@ __device__ __forceinline__ void rb_update(const Geom &g, double *sm, int ly, int
 template <int POW2, int PAR0>
 __global__ void __launch_bounds__(RB_THREADS, RB_MINBLOCKS)
     k_rbgs_fused(Geom g, const double *__restrict__ pin, double *__restrict__ pout, const double *__restrict__ rhs,
-                 Scalars *sc, double *partials, double tol, int ntx) {
+                 Scalars *sc, double *partials, double tol, int ntx, int finish) {
     extern __shared__ double sm_raw[];
     double *sm = sm_raw + RB_PAD; // [2][RB_H][RB_K], padded on both sides
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -83,7 +83,10 @@ __global__ void __launch_bounds__(RB_THREADS, RB_MINBLOCKS)
     int mgx[RB_N][2], mgy[RB_M]; // margin = min(mgx[n][e], mgy[m])
     const size_t o00 = gidx(g, Xe + 2 * lane, Ye + RB_M * warp); // element offset of slot (m = 0, n = 0)
     // A tile whose halo stays inside the interior needs no ghost / domain logic at all (block-uniform branch).
-    const bool edge = Xe < 1 || Xe + RB_W - 1 > g.nx || Ye < 1 || Ye + RB_H - 1 > g.ny || done;
+    // Rows that may be updated: the slab's own cell rows plus, towards a neighbouring slab, the exchanged halo rows
+    // (recomputed redundantly, never stored); rows that may be read: one more (the ghost row / outermost halo row).
+    const int jlo = g.bottom ? 1 : 1 - RB_HY + 1, jhi = g.top ? g.ny : g.ny + RB_HY - 1;
+    const bool edge = Xe < 1 || Xe + RB_W - 1 > g.nx || Ye < jlo || Ye + RB_H - 1 > jhi || done;
 #pragma unroll
     for (int n = 0; n < RB_N; ++n)
 #pragma unroll
@@ -94,7 +97,10 @@ __global__ void __launch_bounds__(RB_THREADS, RB_MINBLOCKS)
 #pragma unroll
     for (int m = 0; m < RB_M; ++m) {
         const int ly = RB_M * warp + m, jj = Ye + ly;
-        mgy[m] = (!edge || (jj >= 1 && jj <= g.ny)) ? min(ly - RB_HY, RB_HY + RB_TY - 1 - ly) : -100;
+        // margin in y: distance inside the output tile AND inside the slab's own rows (halo rows of a neighbouring
+        // slab are recomputed like tile halo, never stored or counted)
+        mgy[m] = !edge ? min(ly - RB_HY, RB_HY + RB_TY - 1 - ly)
+                       : (jj >= jlo && jj <= jhi) ? min(min(ly - RB_HY, RB_HY + RB_TY - 1 - ly), min(jj - 1, g.ny - jj)) : -100;
 #pragma unroll
         for (int n = 0; n < RB_N; ++n) {
             const int k = lane + 32 * n, ii = Xe + 2 * k;
@@ -103,7 +109,7 @@ __global__ void __launch_bounds__(RB_THREADS, RB_MINBLOCKS)
             if (!edge) {
                 pv = *reinterpret_cast<const double2 *>(pin + o);
                 rr = *reinterpret_cast<const double2 *>(rhs + o);
-            } else if (jj >= 0 && jj <= g.ny + 1 && ii >= -1 && ii <= g.nx + 1) { // pair touches the [0, nx+1] box
+            } else if (jj >= jlo - 1 && jj <= jhi + 1 && ii >= -1 && ii <= g.nx + 1) { // pair touches the readable box
                 pv = *reinterpret_cast<const double2 *>(pin + o);
                 rr = *reinterpret_cast<const double2 *>(rhs + o);
                 // ghosts never change during a smooth: carry them (and, when already converged, everything this
@@ -112,7 +118,8 @@ __global__ void __launch_bounds__(RB_THREADS, RB_MINBLOCKS)
                 for (int e = 0; e < 2; ++e) {
                     const int ci = ii + e;
                     if (ci < 0 || ci > g.nx + 1) continue;
-                    const bool ghost = ci == 0 || ci == g.nx + 1 || jj == 0 || jj == g.ny + 1;
+                    if (jj < 0 || jj > g.ny + 1) continue; // deeper halo rows belong to the neighbouring slab
+                    const bool ghost = ci == 0 || ci == g.nx + 1 || (g.bottom && jj == 0) || (g.top && jj == g.ny + 1);
                     if (!ghost && !done) continue;
                     const int ni = min(max(ci, 1), g.nx), nj = min(max(jj, 1), g.ny);
                     const bool mine = ni >= X0 && ni < X0 + RB_TX && nj >= Y0 && nj < Y0 + RB_TY;
@@ -175,9 +182,7 @@ __global__ void __launch_bounds__(RB_THREADS, RB_MINBLOCKS)
     }
     if (pflag) sc->nonfinite_p = 1;
     grid_sum<1>(acc, partials, &sc->ticket[2], [=](double(&t)[1]) {
-        double res = sqrt(t[0]);
-        sc->res = res;
-        sc->iters = sc->iters + 1;
-        if (res < tol) sc->done = 1; // vcycle loop exit, pressure.cpp:120
+        if (finish) rbgs_tail(sc, t[0], tol); // vcycle loop exit, pressure.cpp:120
+        else sc->red[0] = t[0];
     });
 }

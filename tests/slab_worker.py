@@ -1,0 +1,71 @@
+"""One rank of a row-slab run (launched by torchrun from tests/test_gpu_multi.py or by hand):
+
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/slab_worker.py \
+        --preset jet --solver mg --nx 256 --ny 192 --steps 4 --out /tmp/slab.npz
+
+Every rank steps its slab; rank 0 gathers the owned rows, assembles the global u, v, p, rhs and writes them (plus the
+per-step dt / residual / iteration history) to --out.  The caller compares them with a single-GPU run and the oracle.
+"""
+import argparse
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--preset", default="jet")
+    ap.add_argument("--solver", default="mg")
+    ap.add_argument("--nx", type=int, default=256)
+    ap.add_argument("--ny", type=int, default=192)
+    ap.add_argument("--Lx", type=float, default=2.0)
+    ap.add_argument("--Ly", type=float, default=1.0)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--tol", type=float, default=1e-8)
+    ap.add_argument("--iters", type=int, default=200)
+    ap.add_argument("--vcycles", type=int, default=2)
+    ap.add_argument("--variant", type=int, default=1)
+    ap.add_argument("--out", required=True)
+    a = ap.parse_args()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    dist.init_process_group("gloo")  # CPU plumbing only: the id broadcast and the final gather
+    cfd = importlib.import_module("macos-cfd_b200")
+    ids = [cfd.comm_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    s = cfd.Solver(a.nx, a.ny, a.Lx, a.Ly, device=local % torch.cuda.device_count(), rank=rank, nranks=world,
+                   comm_id=ids[0])
+    s.set_variant(a.variant)
+    bc, Re, CFL = cfd.preset(a.preset, a.Ly)
+    pp = cfd.make_params(a.solver, vcycles=a.vcycles, tol=a.tol, pcg_max_iters=a.iters)
+    r0, n = s.row0, s.nrows
+    if a.preset == "shear":
+        s.upload(u=np.ascontiguousarray(cfd.shear_initial_u(a.nx, a.ny, a.Ly)[r0:r0 + n + 2]))
+    hist = []
+    for _ in range(a.steps):
+        info = s.step(bc, Re, CFL, pp)
+        hist.append((info.dt, info.residual, info.iters, info.div_before, info.div_after))
+    div_l2, vmax = s.divergence_l2(), s.max_velocity()
+    u, v, p, rhs = s.download()
+    # owned rows: u, p, rhs local rows 1..n; v rows 1..n (+ n+1 on the top slab); ghost rows from the end slabs
+    top, bottom = rank == world - 1, rank == 0
+    part = {"u": u[(0 if bottom else 1):(n + 2 if top else n + 1)], "v": v[(0 if bottom else 1):(n + 3 if top else n + 1)],
+            "p": p[(0 if bottom else 1):(n + 2 if top else n + 1)], "rhs": rhs[(0 if bottom else 1):(n + 2 if top else n + 1)]}
+    parts = [None] * world
+    dist.gather_object(part, parts if rank == 0 else None, dst=0)
+    if rank == 0:
+        out = {k: np.concatenate([q[k] for q in parts], axis=0) for k in ("u", "v", "p", "rhs")}
+        np.savez(a.out, hist=np.array(hist), div_l2=div_l2, vmax=vmax, **out)
+    s.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,73 @@
+"""Row-slab (multi-GPU) runs against the single-GPU run of the same grid and against the oracle.
+
+Needs >= 2 CUDA devices (run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`); on a 1-GPU
+box every test here is skipped.  Bars: the stencil stages and the whole mg path are BIT-IDENTICAL to
+one GPU; PCG differs only through the order of its inner-product sums (rel-L2 <= 1e-10, iterations +-1).
+"""
+import importlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+def run_slabs(n, tmp_path, **kw):
+    out = str(tmp_path / f"slab_{n}.npz")
+    args = sum([[f"--{k}", str(v)] for k, v in kw.items()], [])
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+           "127.0.0.1", "--master-port", str(29500 + os.getpid() % 500), os.path.join(ROOT, "tests", "slab_worker.py"),
+           "--out", out] + args
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return np.load(out)
+
+
+def run_single(kw):
+    cfd = importlib.import_module("macos-cfd_b200")
+    bc, Re, CFL = cfd.preset(kw["preset"], kw.get("Ly", 1.0))
+    s = cfd.Solver(kw["nx"], kw["ny"], kw.get("Lx", 2.0), kw.get("Ly", 1.0))
+    if kw["preset"] == "shear":
+        s.upload(u=cfd.shear_initial_u(kw["nx"], kw["ny"], kw.get("Ly", 1.0)))
+    pp = cfd.make_params(kw["solver"], vcycles=2, tol=1e-8, pcg_max_iters=kw.get("iters", 200))
+    hist = []
+    for _ in range(kw["steps"]):
+        i = s.step(bc, Re, CFL, pp)
+        hist.append((i.dt, i.residual, i.iters, i.div_before, i.div_after))
+    return np.array(hist), s.download(), s.divergence_l2(), s.max_velocity()
+
+
+def same(a, b):
+    return np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+@pytest.mark.parametrize("preset", ["jet", "lid", "shear"])
+@pytest.mark.parametrize("solver,variant", [("mg", 1), ("mg", 0), ("pcg", 1)])
+def test_slabs_match_single_gpu(tmp_path, preset, solver, variant):
+    n = min(ngpu(), 4)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    kw = dict(preset=preset, solver=solver, nx=260, ny=203, steps=4, iters=60)
+    got = run_slabs(n, tmp_path, variant=variant, **kw)
+    hist, (u, v, p, rhs), div_l2, vmax = run_single(kw)
+    assert np.array_equal(got["hist"][:, 0], hist[:, 0])  # dt
+    assert abs(float(got["vmax"]) - vmax) <= (0.0 if solver == "mg" else 1e-10 * vmax)
+    if solver == "mg":
+        for name, a in (("u", u), ("v", v), ("p", p), ("rhs", rhs)):
+            assert same(got[name], a), name
+        assert np.allclose(got["hist"][:, 1], hist[:, 1], rtol=1e-12)
+    else:
+        assert np.all(np.abs(got["hist"][:, 2] - hist[:, 2]) <= 1)
+        for name, a in (("u", u), ("v", v), ("p", p)):
+            assert np.linalg.norm(got[name] - a) <= 1e-10 * np.linalg.norm(a), name
+    assert abs(float(got["div_l2"]) - div_l2) <= 1e-9 * max(div_l2, 1e-300)
+    assert np.allclose(got["hist"][:, 3:], hist[:, 3:], rtol=1e-9)
