@@ -21,6 +21,8 @@
 #ifndef CFD_B200_H
 #define CFD_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -90,6 +92,10 @@ typedef struct cfd_b200_step_info {
 typedef struct cfd_b200_solver cfd_b200_solver; /* opaque: Grid + device State + PressureSolver + TimeIntegrator */
 
 int cfd_b200_abi_version(void);
+/* Host memory for the caller-owned State: pinned when CUDA is reachable (fast copies), 64-byte aligned otherwise
+ * (Field2D::allocate, field.hpp:35-55).  NULL on failure. */
+void *cfd_b200_host_alloc(size_t bytes);
+void cfd_b200_host_free(void *p);
 const char *cfd_b200_last_error(void);
 /* Number of CUDA devices visible, or a negative error code. */
 int cfd_b200_device_count(void);
@@ -141,14 +147,21 @@ int cfd_b200_max_velocity(cfd_b200_solver *s, double *out);
 int cfd_b200_apply_bc(cfd_b200_solver *s, const cfd_b200_bc *bc, int which);
 /* compute_cfl (metrics.hpp:6) */
 int cfd_b200_compute_cfl(cfd_b200_solver *s, double Re, double CFL, double *dt_out);
-/* advect_u + diffuse_u and advect_v + diffuse_v (advection.hpp:9-10, diffusion.hpp:6-7) of the device u, v,
- * returned in the reference host layout (du: like u, dv: like v).  invRe = 0 gives pure advection. */
+/* The fused right-hand side TimeIntegrator::step uses: sanitize(advect + invRe * diffuse) of the device u, v
+ * (time_integrator.cpp:75-82), returned in the reference host layout (du: like u, dv: like v). */
 int cfd_b200_rhs_terms(cfd_b200_solver *s, double invRe, double *du, double *dv);
+/* advect_u / advect_v alone (advection.hpp:9-10): zero-filled output, advective derivative, not sanitised.
+ * Either pointer may be NULL. */
+int cfd_b200_advect(cfd_b200_solver *s, double *du, double *dv);
+/* diffuse_u (which = 0) / diffuse_v (which = 1) (diffusion.hpp:6-7): d += invRe * laplacian of the device u / v on the
+ * interior set; d is a host array in the layout of u / v, updated in place. */
+int cfd_b200_diffuse(cfd_b200_solver *s, int which, double invRe, double *d);
 /* divergence (project.hpp:8): device rhs = div(u, v) */
 int cfd_b200_divergence(cfd_b200_solver *s);
 /* PressureSolver::solve (pressure.hpp:22) on the device p and rhs */
 int cfd_b200_pressure_solve(cfd_b200_solver *s, const cfd_b200_params *pp, double *residual, int *iters);
-/* subtract_grad_p (project.hpp:12) */
+/* subtract_grad_p (project.hpp:12) on the device u, v, p.  (Inside cfd_b200_step the same kernel also applies the
+ * two p(0,0) = 0 pins of time_integrator.cpp:186-188; this entry point, like the reference function, does not.) */
 int cfd_b200_subtract_grad_p(cfd_b200_solver *s, double dt);
 
 /* ---- measurement ---- */

@@ -139,6 +139,8 @@ def load_library(build: bool = True):
     L.cfd_b200_apply_bc.argtypes = [S, C.POINTER(BC), C.c_int]
     L.cfd_b200_compute_cfl.argtypes = [S, C.c_double, C.c_double, _dp]
     L.cfd_b200_rhs_terms.argtypes = [S, C.c_double, C.c_void_p, C.c_void_p]
+    L.cfd_b200_advect.argtypes = [S, C.c_void_p, C.c_void_p]
+    L.cfd_b200_diffuse.argtypes = [S, C.c_int, C.c_double, C.c_void_p]
     L.cfd_b200_divergence.argtypes = [S]
     L.cfd_b200_pressure_solve.argtypes = [S, C.POINTER(Params), _dp, C.POINTER(C.c_int)]
     L.cfd_b200_subtract_grad_p.argtypes = [S, C.c_double]
@@ -268,6 +270,15 @@ class Solver:
         du, dv = np.empty(sh["u"]), np.empty(sh["v"])
         self._check(self.L.cfd_b200_rhs_terms(self.h, invRe, _addr(du), _addr(dv)))
         return du, dv
+
+    def advect(self):
+        sh = self.shapes()
+        du, dv = np.empty(sh["u"]), np.empty(sh["v"])
+        self._check(self.L.cfd_b200_advect(self.h, _addr(du), _addr(dv)))
+        return du, dv
+
+    def diffuse(self, which, invRe, d):
+        self._check(self.L.cfd_b200_diffuse(self.h, which, invRe, _addr(d)))
 
     def divergence(self):
         self._check(self.L.cfd_b200_divergence(self.h))

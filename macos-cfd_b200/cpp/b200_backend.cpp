@@ -1,0 +1,324 @@
+// b200_backend.cpp -- the reference's solver interface (Grid / Field2D / State / BC / PressureSolver / TimeIntegrator
+// and the public free functions of src/solver/*.hpp) implemented on top of the C ABI.  No solver arithmetic happens
+// here: every function forwards to libcfd_b200.so.  Errors from the device layer become std::runtime_error, except
+// allocation failures, which stay std::bad_alloc like the reference's (field.hpp:46,52).
+#include "b200_backend.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <new>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/cfd_b200.h"
+#include "solver/time_integrator.hpp"
+
+bool tvd_debug = false;
+
+namespace b200 {
+
+struct Session {
+    const Grid *grid = nullptr;
+    cfd_b200_solver *h = nullptr;
+    int refs = 0;
+    // Lazy-mode bookkeeping: which host State the device copy mirrors, and which side is newer
+    const double *host_u = nullptr, *host_v = nullptr;
+    bool host_dirty = true;  // host has data the device has not seen
+    bool host_stale = false; // device is ahead of the host arrays
+    StepReport report;
+    int log_counter = 0;     // time_integrator.cpp:225 (static in the reference)
+    bool warned_sanitize = false, warned_residual = false;
+};
+
+namespace {
+std::map<const Grid *, Session *> g_sessions;
+Coherence g_coherence = Coherence::Eager;
+bool g_coherence_set = false;
+int g_device = -1;
+
+[[noreturn]] void raise(int rc, const char *what) {
+    if (rc == CFD_B200_ENOMEM) throw std::bad_alloc();
+    throw std::runtime_error(std::string(what) + ": " + cfd_b200_last_error());
+}
+void check(int rc, const char *what) {
+    if (rc != 0) raise(rc, what);
+}
+cfd_b200_bc to_c(const BC &bc) {
+    auto side = [](const BCSide &s) { return cfd_b200_bc_side{static_cast<int>(s.type), s.moving, s.inflow_u, s.inflow_v}; };
+    return cfd_b200_bc{side(bc.left), side(bc.right), side(bc.bottom), side(bc.top), bc.jet_center, bc.jet_width};
+}
+cfd_b200_params to_c(const PressureParams &pp) {
+    cfd_b200_params p{};
+    p.solver = pp.type == PressureSolverType::PCG ? CFD_B200_SOLVER_PCG : CFD_B200_SOLVER_MG;
+    p.mg_levels = pp.mg_levels;
+    p.vcycles = pp.vcycles;
+    p.rbgs_sweeps = pp.rbgs_sweeps;
+    p.tol = pp.tol;
+    p.pcg_max_iters = pp.pcg_max_iters;
+    p.mg_mode = pp.true_vcycle ? CFD_B200_MG_VCYCLE : CFD_B200_MG_REFERENCE;
+    return p;
+}
+// A short-lived session for the stage-level free functions, which get arbitrary host arrays.
+struct Scratch {
+    Session *s;
+    explicit Scratch(const Grid &g) : s(acquire(g)) {}
+    ~Scratch() { release(s); }
+    cfd_b200_solver *h() const { return s->h; }
+};
+} // namespace
+
+void set_coherence(Coherence c) { g_coherence = c, g_coherence_set = true; }
+Coherence coherence() {
+    if (!g_coherence_set) {
+        const char *e = std::getenv("CFD_B200_COHERENCE");
+        if (e && std::strcmp(e, "lazy") == 0) g_coherence = Coherence::Lazy;
+        g_coherence_set = true;
+    }
+    return g_coherence;
+}
+void set_device(int device) { g_device = device; }
+
+Session *acquire(const Grid &g) {
+    auto it = g_sessions.find(&g);
+    if (it != g_sessions.end()) {
+        it->second->refs++;
+        return it->second;
+    }
+    if (g.ngx != 1 || g.ngy != 1) throw std::runtime_error("cfd_b200: only ng = 1 is supported (the reference's value)");
+    int dev = g_device;
+    if (dev < 0) {
+        const char *e = std::getenv("CFD_B200_DEVICE");
+        dev = e ? std::atoi(e) : 0;
+    }
+    Session *s = new Session;
+    s->grid = &g;
+    s->refs = 1;
+    int rc = cfd_b200_create(g.nx, g.ny, g.Lx, g.Ly, dev, &s->h);
+    if (rc != 0) {
+        delete s;
+        raise(rc, "cfd_b200_create");
+    }
+    g_sessions[&g] = s;
+    return s;
+}
+void release(Session *s) {
+    if (!s || --s->refs > 0) return;
+    g_sessions.erase(s->grid);
+    cfd_b200_destroy(s->h);
+    delete s;
+}
+cfd_b200_solver *handle(Session *s) { return s->h; }
+
+static Session *find_by_state(const double *u, const double *v) {
+    for (auto &kv : g_sessions)
+        if (kv.second->host_u == u && kv.second->host_v == v) return kv.second;
+    return nullptr;
+}
+void mark_host_dirty(const State &st) {
+    if (Session *s = find_by_state(st.u.data, st.v.data)) s->host_dirty = true, s->host_stale = false;
+}
+void sync_to_host(State &st) {
+    Session *s = find_by_state(st.u.data, st.v.data);
+    if (!s || !s->host_stale) return;
+    check(cfd_b200_download(s->h, st.u.data, st.v.data, st.p.data, st.rhs.data), "cfd_b200_download");
+    s->host_stale = false;
+}
+StepReport last_report(const Grid &g) {
+    auto it = g_sessions.find(&g);
+    return it == g_sessions.end() ? StepReport{} : it->second->report;
+}
+
+} // namespace b200
+
+using b200::check;
+
+// ------------------------------------------------------------------------------------------------ PressureSolver
+PressureSolver::PressureSolver(const Grid &grid) : g(grid), session_(b200::acquire(grid)) {}
+PressureSolver::~PressureSolver() { b200::release(session_); }
+
+double PressureSolver::solve(Field2D<double> &p, const Field2D<double> &rhs, const PressureParams &params) {
+    cfd_b200_solver *h = session_->h;
+    check(cfd_b200_upload(h, nullptr, nullptr, p.data), "cfd_b200_upload");
+    check(cfd_b200_upload_rhs(h, rhs.data), "cfd_b200_upload_rhs");
+    cfd_b200_params pp = b200::to_c(params);
+    double res = 0.0;
+    check(cfd_b200_pressure_solve(h, &pp, &res, &last_iters_), "cfd_b200_pressure_solve");
+    check(cfd_b200_download(h, nullptr, nullptr, p.data, nullptr), "cfd_b200_download");
+    if (res == 1e9 && !warned_nan_) { // pressure.cpp:124-127, :233-236
+        std::fprintf(stderr, "Non-finite pressure residual\n");
+        warned_nan_ = true;
+    }
+    last_residual_ = res;
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------------ TimeIntegrator
+TimeIntegrator::TimeIntegrator(const Grid &grid) : g(grid), session_(b200::acquire(grid)) {
+    du_dt.allocate(g.u_nx(), g.ny, g.u_pitch(), g.ngx, g.ngy);
+    dv_dt.allocate(g.nx, g.v_ny(), g.v_pitch(), g.ngx, g.ngy);
+    u1.allocate(g.u_nx(), g.ny, g.u_pitch(), g.ngx, g.ngy);
+    v1.allocate(g.nx, g.v_ny(), g.v_pitch(), g.ngx, g.ngy);
+    clear_work();
+}
+TimeIntegrator::~TimeIntegrator() { b200::release(session_); }
+
+void TimeIntegrator::clear_work() {
+    std::memset(du_dt.data, 0, du_dt.count() * sizeof(double));
+    std::memset(dv_dt.data, 0, dv_dt.count() * sizeof(double));
+    std::memset(u1.data, 0, u1.count() * sizeof(double));
+    std::memset(v1.data, 0, v1.count() * sizeof(double));
+    check(cfd_b200_clear_work(session_->h), "cfd_b200_clear_work");
+}
+
+double TimeIntegrator::step(State &s, const BC &bc, double Re, double CFL, PressureSolver &pressure,
+                            const PressureParams &pp, double &pressure_residual, double dt_override) {
+    b200::Session *ss = session_;
+    cfd_b200_solver *h = ss->h;
+    const bool lazy = b200::coherence() == b200::Coherence::Lazy;
+    const bool same_state = ss->host_u == s.u.data && ss->host_v == s.v.data;
+    if (!lazy || !same_state || ss->host_dirty) {
+        check(cfd_b200_upload(h, s.u.data, s.v.data, s.p.data), "cfd_b200_upload");
+        ss->host_u = s.u.data, ss->host_v = s.v.data;
+        ss->host_dirty = false;
+    }
+    cfd_b200_bc cbc = b200::to_c(bc);
+    cfd_b200_params cpp = b200::to_c(pp);
+    cfd_b200_step_info info{};
+    check(cfd_b200_step(h, &cbc, Re, CFL, &cpp, dt_override, &info), "cfd_b200_step");
+    if (lazy) {
+        ss->host_stale = true;
+    } else {
+        check(cfd_b200_download(h, s.u.data, s.v.data, s.p.data, s.rhs.data), "cfd_b200_download");
+        ss->host_stale = false;
+    }
+    // the reference's observable side effects: stderr messages with the same text and cadence
+    if ((info.nonfinite & 1) && !ss->warned_sanitize) { // time_integrator.cpp:20-25
+        std::fprintf(stderr, "Non-finite values detected and replaced with 0\n");
+        ss->warned_sanitize = true;
+    }
+    if (info.pcg_breakdown >= 0) std::fprintf(stderr, "PCG breakdown at iteration %d\n", info.pcg_breakdown); // pressure.cpp:184
+    if ((info.nonfinite & 2) && !ss->warned_residual) {
+        std::fprintf(stderr, "Non-finite pressure residual\n");
+        ss->warned_residual = true;
+    }
+    if (info.div_before > 1e-12) { // time_integrator.cpp:223-231
+        if (ss->log_counter % 60 == 0)
+            std::fprintf(stderr, "Divergence: before=%.2e, after=%.2e, reduction=%.1fx\n", info.div_before, info.div_after,
+                         info.div_before / info.div_after);
+        ss->log_counter++;
+    }
+    ss->report = {info.dt, info.residual, info.div_before, info.div_after, info.iters, info.pcg_breakdown, info.nonfinite};
+    pressure.last_residual_ = info.residual;
+    pressure.last_iters_ = info.iters;
+    pressure_residual = info.residual;
+    return info.dt;
+}
+
+void sanitize_field(Field2D<double> &f) { // host utility on a host array (time_integrator.cpp:8-27)
+    bool any = false;
+    for (size_t i = 0, n = f.count(); i < n; ++i)
+        if (!std::isfinite(f.data[i])) f.data[i] = 0.0, any = true;
+    static bool warned = false;
+    if (any && !warned) {
+        std::fprintf(stderr, "Non-finite values detected and replaced with 0\n");
+        warned = true;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ free functions
+// Diagnostics the drivers call after every step (main.cpp:151, :255-256).  When the arrays are the State a session
+// mirrors and the device copy is newer (lazy mode), they are answered from the device without any transfer.
+static double diagnostic(const Grid &g, const Field2D<double> &u, const Field2D<double> &v, bool want_max) {
+    b200::Session *own = b200::find_by_state(u.data, v.data);
+    double out = 0.0;
+    if (own && own->host_stale) {
+        check(want_max ? cfd_b200_max_velocity(own->h, &out) : cfd_b200_divergence_l2(own->h, &out), "diagnostic");
+        return out;
+    }
+    b200::Scratch sc(g);
+    check(cfd_b200_upload(sc.h(), u.data, v.data, nullptr), "cfd_b200_upload");
+    if (own) own->host_dirty = true; // the shared session's device State was overwritten with these arrays
+    check(want_max ? cfd_b200_max_velocity(sc.h(), &out) : cfd_b200_divergence_l2(sc.h(), &out), "diagnostic");
+    return out;
+}
+double divergence_l2(const Grid &g, const Field2D<double> &u, const Field2D<double> &v) { return diagnostic(g, u, v, false); }
+double max_velocity(const Grid &g, const Field2D<double> &u, const Field2D<double> &v) { return diagnostic(g, u, v, true); }
+
+// The remaining public functions of the reference headers operate on caller arrays: upload, run the stage kernel,
+// download.  They exist for source compatibility and kernel-level tests, not for speed.
+namespace {
+struct StageGuard { // the session's device State is about to be overwritten by unrelated arrays
+    b200::Scratch sc;
+    explicit StageGuard(const Grid &g) : sc(g) { sc.s->host_dirty = true, sc.s->host_stale = false; }
+    cfd_b200_solver *h() const { return sc.h(); }
+};
+} // namespace
+
+double jet_velocity(const Grid &, const BC &bc, double y) { // bc.cpp:7-29 (host helper used by GUI previews)
+    return bc.left.inflow_u * ((std::fabs(y - bc.jet_center) <= 0.5 * bc.jet_width) ? 1.0 : 0.0);
+}
+void apply_bc_u(const Grid &g, Field2D<double> &u, const BC &bc) {
+    StageGuard s(g);
+    cfd_b200_bc c = b200::to_c(bc);
+    check(cfd_b200_upload(s.h(), u.data, nullptr, nullptr), "upload");
+    check(cfd_b200_apply_bc(s.h(), &c, 1), "cfd_b200_apply_bc");
+    check(cfd_b200_download(s.h(), u.data, nullptr, nullptr, nullptr), "download");
+}
+void apply_bc_v(const Grid &g, Field2D<double> &v, const BC &bc) {
+    StageGuard s(g);
+    cfd_b200_bc c = b200::to_c(bc);
+    check(cfd_b200_upload(s.h(), nullptr, v.data, nullptr), "upload");
+    check(cfd_b200_apply_bc(s.h(), &c, 2), "cfd_b200_apply_bc");
+    check(cfd_b200_download(s.h(), nullptr, v.data, nullptr, nullptr), "download");
+}
+void apply_bc_p(const Grid &g, Field2D<double> &p, const BC &bc) {
+    StageGuard s(g);
+    cfd_b200_bc c = b200::to_c(bc);
+    check(cfd_b200_upload(s.h(), nullptr, nullptr, p.data), "upload");
+    check(cfd_b200_apply_bc(s.h(), &c, 4), "cfd_b200_apply_bc");
+    check(cfd_b200_download(s.h(), nullptr, nullptr, p.data, nullptr), "download");
+}
+double compute_cfl(const Grid &g, const Field2D<double> &u, const Field2D<double> &v, double Re, double CFL_target) {
+    StageGuard s(g);
+    double dt = 0.0;
+    check(cfd_b200_upload(s.h(), u.data, v.data, nullptr), "upload");
+    check(cfd_b200_compute_cfl(s.h(), Re, CFL_target, &dt), "cfd_b200_compute_cfl");
+    return dt;
+}
+// advect_* zero-fill the output and write the advective derivative (advection.cpp:33-421); diffuse_* ADD
+// invRe * laplacian to an existing derivative on the interior set (diffusion.cpp:5-39).
+void advect_u(const Grid &g, const Field2D<double> &u, const Field2D<double> &v, Field2D<double> &du_dt) {
+    StageGuard s(g);
+    check(cfd_b200_upload(s.h(), u.data, v.data, nullptr), "upload");
+    check(cfd_b200_advect(s.h(), du_dt.data, nullptr), "cfd_b200_advect");
+}
+void advect_v(const Grid &g, const Field2D<double> &u, const Field2D<double> &v, Field2D<double> &dv_dt) {
+    StageGuard s(g);
+    check(cfd_b200_upload(s.h(), u.data, v.data, nullptr), "upload");
+    check(cfd_b200_advect(s.h(), nullptr, dv_dt.data), "cfd_b200_advect");
+}
+void diffuse_u(const Grid &g, const Field2D<double> &u, Field2D<double> &du_dt, double invRe) {
+    StageGuard s(g);
+    check(cfd_b200_upload(s.h(), u.data, nullptr, nullptr), "upload");
+    check(cfd_b200_diffuse(s.h(), 0, invRe, du_dt.data), "cfd_b200_diffuse");
+}
+void diffuse_v(const Grid &g, const Field2D<double> &v, Field2D<double> &dv_dt, double invRe) {
+    StageGuard s(g);
+    check(cfd_b200_upload(s.h(), nullptr, v.data, nullptr), "upload");
+    check(cfd_b200_diffuse(s.h(), 1, invRe, dv_dt.data), "cfd_b200_diffuse");
+}
+void divergence(const Grid &g, const Field2D<double> &u, const Field2D<double> &v, Field2D<double> &rhs) {
+    StageGuard s(g);
+    check(cfd_b200_upload(s.h(), u.data, v.data, nullptr), "upload");
+    check(cfd_b200_divergence(s.h()), "cfd_b200_divergence");
+    check(cfd_b200_download(s.h(), nullptr, nullptr, nullptr, rhs.data), "download");
+}
+void subtract_grad_p(const Grid &g, Field2D<double> &u, Field2D<double> &v, const Field2D<double> &p, double dt) {
+    StageGuard s(g);
+    check(cfd_b200_upload(s.h(), u.data, v.data, p.data), "upload");
+    check(cfd_b200_subtract_grad_p(s.h(), dt), "cfd_b200_subtract_grad_p");
+    check(cfd_b200_download(s.h(), u.data, v.data, nullptr, nullptr), "download");
+}

@@ -353,11 +353,11 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
     return 0;
 }
 
-void enqueue_project(cfd_b200_solver *s, const Scalars *dt_src, double dt_arg) {
+void enqueue_project(cfd_b200_solver *s, const Scalars *dt_src, double dt_arg, int pin = 1) {
     const Geom &g = s->g;
     int rpb = 4;
     dim3 grid = row_grid(s, cdiv(g.nx + 1, 2), g.ny + 1, &rpb);
-    LAUNCH(s, k_project, grid, 256, g, s->u, s->v, s->p, dt_src, dt_arg, s->d_sc, rpb);
+    LAUNCH(s, k_project, grid, 256, g, s->u, s->v, s->p, dt_src, dt_arg, s->d_sc, rpb, pin);
 }
 
 // TimeIntegrator::step, time_integrator.cpp:47-239
@@ -452,6 +452,27 @@ int need_scratch(cfd_b200_solver *s) {
 } // namespace
 
 extern "C" {
+
+// Pinned host memory for the caller-owned State (Field2D::allocate of the C++ layer): host<->device copies of the
+// drop-in then run at full PCIe speed.  Falls back to aligned_alloc when no CUDA runtime/device is reachable.
+void *cfd_b200_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (bytes == 0) bytes = 64;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) return p; // page aligned
+    cudaGetLastError();
+    p = aligned_alloc(64, (bytes + 63) / 64 * 64);
+    return p;
+}
+void cfd_b200_host_free(void *p) {
+    if (!p) return;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeHost) {
+        cudaFreeHost(p);
+        return;
+    }
+    cudaGetLastError();
+    free(p);
+}
 
 int cfd_b200_abi_version(void) { return CFD_B200_ABI_VERSION; }
 const char *cfd_b200_last_error(void) { return g_err; }
@@ -718,6 +739,44 @@ int cfd_b200_rhs_terms(cfd_b200_solver *s, double invRe, double *du, double *dv)
     return 0;
 }
 
+int cfd_b200_advect(cfd_b200_solver *s, double *du, double *dv) {
+    if (!s || (!du && !dv)) return fail(CFD_B200_EINVAL, "NULL argument");
+    if (s->nranks > 1) return fail(CFD_B200_EUNSUPPORTED, "stage-level entry points are single-GPU");
+    CU(cudaSetDevice(s->device));
+    int rc = need_scratch(s);
+    if (rc) return rc;
+    const Geom &g = s->g;
+    CU(cudaMemsetAsync(s->scratch_u, 0, s->n * sizeof(double), s->stream)); // advect_* zero-fill first (advection.cpp:41)
+    CU(cudaMemsetAsync(s->scratch_v, 0, s->n * sizeof(double), s->stream));
+    RhsConst k{g.idx, g.idy, g.idx2, g.idy2, 0.0};
+    dim3 grid(cdiv(g.nx + 1, RHS_TX), cdiv(g.ny + 1, RHS_TY)), block(RHS_TX, RHS_TY);
+    LAUNCH(s, k_rhs_simple<3>, grid, block, g, k, s->u, s->v, s->scratch_u, s->scratch_v, s->d_sc, 0, 0);
+    if (du && (rc = copy_field(s, s->scratch_u, du, g.nx + 3, g.ny + 2, false))) return rc;
+    if (dv && (rc = copy_field(s, s->scratch_v, dv, g.nx + 2, g.ny + 3, false))) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int cfd_b200_diffuse(cfd_b200_solver *s, int which, double invRe, double *d) {
+    if (!s || !d || (which != 0 && which != 1)) return fail(CFD_B200_EINVAL, "bad argument");
+    if (s->nranks > 1) return fail(CFD_B200_EUNSUPPORTED, "stage-level entry points are single-GPU");
+    CU(cudaSetDevice(s->device));
+    int rc = need_scratch(s);
+    if (rc) return rc;
+    const Geom &g = s->g;
+    double *scratch = which ? s->scratch_v : s->scratch_u;
+    const int pitch = which ? g.nx + 2 : g.nx + 3, rows = which ? g.ny + 3 : g.ny + 2;
+    const int IX = which ? g.nx : g.nx + 1, JY = which ? g.ny + 1 : g.ny;
+    if ((rc = copy_field(s, scratch, d, pitch, rows, true))) return rc;
+    if (IX > 2 && JY > 2)
+        LAUNCH(s, k_diffuse_add, dim3(cdiv(IX - 2, 128), JY - 2), 128, g, which ? s->v : s->u, scratch, invRe, IX, JY);
+    if ((rc = copy_field(s, scratch, d, pitch, rows, false))) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int cfd_b200_divergence(cfd_b200_solver *s) {
     if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
     CU(cudaSetDevice(s->device));
@@ -744,7 +803,7 @@ int cfd_b200_subtract_grad_p(cfd_b200_solver *s, double dt) {
     if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
     CU(cudaSetDevice(s->device));
     s->cfl_cached = false;
-    enqueue_project(s, nullptr, dt);
+    enqueue_project(s, nullptr, dt, 0);
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
     return 0;

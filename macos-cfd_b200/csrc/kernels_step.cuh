@@ -233,10 +233,21 @@ struct RhsConst {
     double idx, idy, idx2, idy2, invRe;
 };
 
+// diffuse_u / diffuse_v as free functions (diffusion.cpp:5-39): out += invRe * laplacian(q) on the advection
+// interior set ii in [2, IX-1], jj in [2, JY-1]; nothing else is touched.
+__global__ void k_diffuse_add(Geom g, const double *__restrict__ q, double *out, double invRe, int IX, int JY) {
+    const int ii = 2 + blockIdx.x * blockDim.x + threadIdx.x, jj = 2 + blockIdx.y;
+    if (ii > IX - 1 || jj > JY - 1) return;
+    const size_t o = gidx(g, ii, jj);
+    double lap = (q[o + 1] - 2.0 * q[o] + q[o - 1]) * g.idx2 + (q[o + g.P] - 2.0 * q[o] + q[o - g.P]) * g.idy2;
+    out[o] += invRe * lap;
+}
+
 // d(q)/dt at one face.  qc/uc/vc point at (ii,jj) of the q/u/v tiles (row stride S).  In raw indices both
 // advect_u and advect_v carry q with x-face velocities u(ii,jj), u(ii-1,jj) and y-face velocities v(ii,jj),
 // v(ii,jj-1) (advection.cpp:68,80,101,113 and :263,275,296,308).  ex/ey = -1/0/+1 mark the first-order ring
 // (advection.cpp:124-225, :319-419); corner faces stay 0 and get no diffusion (diffusion.cpp:12-13).
+template <bool DIFFUSE = true>
 __device__ __forceinline__ double rhs_point(const double *qc, const double *uc, const double *vc, int S, int ex,
                                             int ey, const RhsConst &k) {
     if (ex != 0 && ey != 0) return 0.0;
@@ -251,7 +262,7 @@ __device__ __forceinline__ double rhs_point(const double *qc, const double *uc, 
         double conv = (fxp - fxm) * k.idx + (fyp - fym) * k.idy;
         double lap = (qc[1] - 2.0 * c + qc[-1]) * k.idx2 + (qc[S] - 2.0 * c + qc[-S]) * k.idy2;
         d = -conv;
-        d = d + k.invRe * lap; // du_dt += invRe * lap
+        if (DIFFUSE) d = d + k.invRe * lap; // du_dt += invRe * lap
     } else {
         double fxp = (ex == 1) ? 0.0 : upwind1(c, qc[1], wxp);
         double fxm = (ex == -1) ? 0.0 : upwind1(qc[-1], c, wxm);
@@ -267,6 +278,7 @@ __device__ __forceinline__ double rhs_point(const double *qc, const double *uc, 
 // MODE 1: RK stage 1   out = sanitize(in + dt * sanitize(d))                 (time_integrator.cpp:81-103)
 // MODE 2: RK stage 2   acc = sanitize(0.5 * (acc + in + dt * sanitize(d)))   (time_integrator.cpp:119-147)
 //         (in = u1/v1 is the field the derivative is taken of; acc = s.u/s.v, updated in place)
+// MODE 3: advect_u / advect_v as free functions: the advective derivative only, not sanitised
 #define RHS_TX 32
 #define RHS_TY 8
 template <int MODE>
@@ -293,24 +305,26 @@ __global__ void __launch_bounds__(RHS_TX *RHS_TY)
     __syncthreads();
     const int ii = x0 + threadIdx.x, jj = y0 + threadIdx.y;
     const int c = (threadIdx.y + 2) * S + threadIdx.x + 2;
-    const double dt = (MODE == 0) ? 0.0 : sc->dt;
+    const double dt = (MODE == 0 || MODE == 3) ? 0.0 : sc->dt;
     int flag = 0;
     const int JYv = v_rows(g);
     if (ii <= g.nx + 1 && jj <= g.ny) { // u faces: ii in [1, nx+1], jj in [1, ny]
         int ex = (ii == 1) ? -1 : (ii == g.nx + 1) ? 1 : 0;
         int ey = (g.bottom && jj == 1) ? -1 : (g.top && jj == g.ny) ? 1 : 0;
-        double d = sanitize_val(rhs_point(us + c, us + c, vs + c, S, ex, ey, k), flag);
+        double d = (MODE == 3) ? rhs_point<false>(us + c, us + c, vs + c, S, ex, ey, k)
+                               : sanitize_val(rhs_point(us + c, us + c, vs + c, S, ex, ey, k), flag);
         size_t o = gidx(g, ii, jj);
-        if (MODE == 0) uout[o] = d;
+        if (MODE == 0 || MODE == 3) uout[o] = d;
         if (MODE == 1) uout[o] = sanitize_val(us[c] + dt * d, flag);
         if (MODE == 2) uout[o] = sanitize_val(0.5 * (uout[o] + us[c] + dt * d), flag);
     }
     if (ii <= g.nx && jj <= JYv) { // v faces: ii in [1, nx], jj in [1, ny+1]
         int ex = (ii == 1) ? -1 : (ii == g.nx) ? 1 : 0;
         int ey = (g.bottom && jj == 1) ? -1 : (g.top && jj == g.ny + 1) ? 1 : 0;
-        double d = sanitize_val(rhs_point(vs + c, us + c, vs + c, S, ex, ey, k), flag);
+        double d = (MODE == 3) ? rhs_point<false>(vs + c, us + c, vs + c, S, ex, ey, k)
+                               : sanitize_val(rhs_point(vs + c, us + c, vs + c, S, ex, ey, k), flag);
         size_t o = gidx(g, ii, jj);
-        if (MODE == 0) vout[o] = d;
+        if (MODE == 0 || MODE == 3) vout[o] = d;
         if (MODE == 1) vout[o] = sanitize_val(vs[c] + dt * d, flag);
         if (MODE == 2) vout[o] = sanitize_val(0.5 * (vout[o] + vs[c] + dt * d), flag);
     }
@@ -379,7 +393,7 @@ __global__ void __launch_bounds__(256)
 // =========================================================================================================
 __global__ void __launch_bounds__(256)
     k_project(Geom g, double *__restrict__ u, double *__restrict__ v, double *p, const Scalars *sc, double dt_arg,
-              Scalars *flags, int rpb) {
+              Scalars *flags, int rpb, int pin) {
     // One thread = two adjacent columns (aligned double2) marching up rpb rows; the p pair of the row below is
     // carried in registers, p(ii-1) comes from the left lane.
     const int ii = 1 + 2 * (blockIdx.x * blockDim.x + threadIdx.x);
@@ -387,7 +401,7 @@ __global__ void __launch_bounds__(256)
     const double dt = sc ? sc->dt : dt_arg;
     const int jbase = 1 + blockIdx.y * rpb;
     const int JYv = v_rows(g);
-    const bool pin_here = (g.j0 == 0);
+    const bool pin_here = pin && (g.j0 == 0); // the pins belong to TimeIntegrator::step, not to subtract_grad_p
     const bool u_b = ii + 1 <= g.nx + 1, v_a = ii <= g.nx, v_b = ii + 1 <= g.nx; // which faces of the pair exist
     int flag = 0;
     double2 pb = make_double2(0.0, 0.0);

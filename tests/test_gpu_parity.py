@@ -134,14 +134,24 @@ def test_stage_kernels_bit_exact(cfd, port, nx, ny, Lx, Ly, variant):
     gd, od = s.divergence_l2(), port.divergence_l2(nx, ny, Lx, Ly, u, v)
     assert gd == od or abs(gd - od) <= 1e-13 * abs(od)  # (the 1e300 sentinels make both inf)
     assert s.max_velocity() == port.max_velocity(nx, ny, Lx, Ly, u, v)
-    # subtract_grad_p (p(0,0) pinned as in TimeIntegrator::step)
-    p0 = p.copy()
-    p0[1, 1] = 0.0
+    # subtract_grad_p
     u2, v2 = u.copy(), v.copy()
-    port.subtract_grad_p(nx, ny, Lx, Ly, u2, v2, p0, 3e-4)
+    port.subtract_grad_p(nx, ny, Lx, Ly, u2, v2, p, 3e-4)
     s.subtract_grad_p(3e-4)
     gu, gv, gp, _ = s.download()
-    assert same(gu, u2) and same(gv, v2) and same(gp, p0)
+    assert same(gu, u2) and same(gv, v2) and same(gp, p)
+    # advect_* / diffuse_* as separate free functions (no sanitise, diffusion ADDS to its argument)
+    s.upload(u, v, p)
+    du, dv = np.full_like(u, 9.0), np.full_like(v, 9.0)
+    port.advect_u(nx, ny, Lx, Ly, u, v, du)
+    port.advect_v(nx, ny, Lx, Ly, u, v, dv)
+    gdu, gdv = s.advect()
+    assert same(gdu, du) and same(gdv, dv)
+    port.diffuse_u(nx, ny, Lx, Ly, u, du, 0.02)
+    port.diffuse_v(nx, ny, Lx, Ly, v, dv, 0.02)
+    s.diffuse(0, 0.02, gdu)
+    s.diffuse(1, 0.02, gdv)
+    assert same(gdu, du) and same(gdv, dv)
 
 
 @pytest.mark.parametrize("nx,ny,Lx,Ly", [(16, 16, 1.0, 1.0), (37, 21, 2.0, 0.9), (64, 32, 2.0, 1.0), (130, 67, 1.0, 1.0)])
