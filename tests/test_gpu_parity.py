@@ -33,6 +33,13 @@ def same(a, b):
     return np.array_equal(a.view(np.uint64), b.view(np.uint64))
 
 
+def same_or_nan(a, b):
+    """Bitwise equal, except that a NaN matches any NaN (sign / payload bits of a NaN are implementation-defined
+    and differ between x86 and the GPU).  Only for UNSANITISED outputs; the solver path itself never stores a NaN."""
+    both_nan = np.isnan(a) & np.isnan(b)
+    return bool(np.all((a.view(np.uint64) == b.view(np.uint64)) | both_nan))
+
+
 def nbad(a, b):
     return int(np.count_nonzero(a.view(np.uint64) != b.view(np.uint64)))
 
@@ -146,12 +153,12 @@ def test_stage_kernels_bit_exact(cfd, port, nx, ny, Lx, Ly, variant):
     port.advect_u(nx, ny, Lx, Ly, u, v, du)
     port.advect_v(nx, ny, Lx, Ly, u, v, dv)
     gdu, gdv = s.advect()
-    assert same(gdu, du) and same(gdv, dv)
+    assert same_or_nan(gdu, du) and same_or_nan(gdv, dv)
     port.diffuse_u(nx, ny, Lx, Ly, u, du, 0.02)
     port.diffuse_v(nx, ny, Lx, Ly, v, dv, 0.02)
     s.diffuse(0, 0.02, gdu)
     s.diffuse(1, 0.02, gdv)
-    assert same(gdu, du) and same(gdv, dv)
+    assert same_or_nan(gdu, du) and same_or_nan(gdv, dv)
 
 
 @pytest.mark.parametrize("nx,ny,Lx,Ly", [(16, 16, 1.0, 1.0), (37, 21, 2.0, 0.9), (64, 32, 2.0, 1.0), (130, 67, 1.0, 1.0)])
