@@ -16,6 +16,7 @@
 #include "kernels_step.cuh"
 #include "kernels_rhs_march.cuh"
 #include "kernels_rbgs_fused.cuh"
+#include "kernels_vcycle.cuh"
 
 namespace {
 
@@ -47,6 +48,7 @@ struct cfd_b200_solver {
     Geom g{};
     int device = 0;
     int rank = 0, nranks = 1;
+    double Lx = 1.0, Ly = 1.0;
     size_t n = 0; // doubles per field
     double *u = nullptr, *v = nullptr, *p = nullptr, *rhs = nullptr;
     double *p_alt = nullptr; // ping-pong partner of p for the fused red-black smoother
@@ -67,6 +69,10 @@ struct cfd_b200_solver {
     bool ev_valid = false;
     int sm_count = 148;
     ncclComm_t comm = nullptr; // row slabs only
+    // V-cycle extension: coarse levels (level 0 aliases p / rhs), allocated on first use
+    int mg_nlev = 0;
+    MgLevel mg[MG_CTA_MAXLEV + 4] = {};
+    int mg_cta_smem_max = 0;
 };
 
 namespace {
@@ -271,6 +277,99 @@ void launch_fused(cfd_b200_solver *s, double tol, int ntx, int nty, int finish) 
     s->launches++;
 }
 
+// ---- EXTENSION: true geometric V-cycle (kernels_vcycle.cuh; algorithm = oracle/cfd_vcycle.c; parity unpinned) ----
+int vcycle_levels(int nx, int ny, int mg_levels) {
+    int n = 1;
+    while (n < mg_levels && n < MG_CTA_MAXLEV + 3 && nx % 2 == 0 && ny % 2 == 0 && nx / 2 >= 4 && ny / 2 >= 4) nx /= 2, ny /= 2, ++n;
+    return n;
+}
+int enqueue_vcycle(cfd_b200_solver *s, const cfd_b200_params *pp, double Lx, double Ly) {
+    const Geom &g = s->g;
+    if (s->nranks > 1) return fail(CFD_B200_EUNSUPPORTED, "mg_mode=VCYCLE is single-GPU in this version");
+    const int nlev = vcycle_levels(g.nx, g.ny, pp->mg_levels);
+    const int sweeps = pp->rbgs_sweeps;
+    for (int l = 0; l < nlev; ++l) { // geometry of every level exactly as the restatement computes it
+        MgLevel &L = s->mg[l];
+        const int nx = g.nx >> l, ny = g.ny >> l;
+        if (l > 0 && (L.nx != nx || L.ny != ny || !L.p)) {
+            if (L.p) cudaFree(L.p), cudaFree(L.rhs);
+            L.P = ((nx + 3 + CFD_XOFF + 2) + 15) / 16 * 16;
+            const size_t n = (size_t)L.P * (ny + 3 + 2 * CFD_YOFF);
+            CU(cudaMalloc(&L.p, n * sizeof(double)));
+            CU(cudaMalloc(&L.rhs, n * sizeof(double)));
+            CU(cudaMemsetAsync(L.p, 0, n * sizeof(double), s->stream));
+            CU(cudaMemsetAsync(L.rhs, 0, n * sizeof(double), s->stream));
+        }
+        L.nx = nx;
+        L.ny = ny;
+        const double dx = Lx / static_cast<double>(nx), dy = Ly / static_cast<double>(ny);
+        L.idx2 = 1.0 / (dx * dx);
+        L.idy2 = 1.0 / (dy * dy);
+        L.denom = 2.0 * (L.idx2 + L.idy2);
+        if (l == 0) L.P = g.P, L.p = s->p, L.rhs = s->rhs;
+    }
+    if (nlev > s->mg_nlev) s->mg_nlev = nlev;
+    // first level that (with everything below it) fits into one block's shared memory
+    MgCtaPlan plan{};
+    int lc = nlev;
+    for (int l = 1; l < nlev; ++l) {
+        size_t doubles = 0;
+        for (int m = l; m < nlev; ++m) doubles += 2 * (size_t)(s->mg[m].nx + 2) * (s->mg[m].ny + 2);
+        if (doubles * 8 <= 200 * 1024 && nlev - l <= MG_CTA_MAXLEV) {
+            lc = l;
+            break;
+        }
+    }
+    int cta_smem = 0;
+    if (lc < nlev) {
+        plan.nlev = nlev - lc;
+        plan.sweeps = sweeps;
+        int off = 0;
+        for (int m = lc; m < nlev; ++m) {
+            const MgLevel &L = s->mg[m];
+            const int k = m - lc;
+            plan.nx[k] = L.nx, plan.ny[k] = L.ny, plan.off[k] = off;
+            plan.idx2[k] = L.idx2, plan.idy2[k] = L.idy2, plan.denom[k] = L.denom;
+            off += 2 * (L.nx + 2) * (L.ny + 2);
+        }
+        cta_smem = off * 8;
+        if (cta_smem > s->mg_cta_smem_max) {
+            CU(cudaFuncSetAttribute(k_mg_coarse_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, cta_smem));
+            s->mg_cta_smem_max = cta_smem;
+        }
+    }
+    auto smooth = [&](const MgLevel &L, int n) {
+        dim3 block(32, 8), grid(cdiv(cdiv(L.nx + 1, 2), 32), cdiv(L.ny, 8));
+        for (int k = 0; k < n; ++k)
+            for (int colour = 0; colour < 2; ++colour) LAUNCH(s, k_mg_colour, grid, block, L, colour, s->d_sc);
+    };
+    LAUNCH(s, k_solve_begin, 1, 1, s->d_sc);
+    LAUNCH(s, k_mg_zero_ghosts, cdiv((g.nx > g.ny ? g.nx : g.ny) + 2, 128), 128, s->mg[0], s->d_sc);
+    const int top = lc < nlev ? lc : nlev - 1; // levels [0, top) run as global-memory kernels on the way down
+    for (int vc = 0; vc < pp->vcycles; ++vc) {
+        for (int l = 0; l < top; ++l) {
+            smooth(s->mg[l], sweeps);
+            const MgLevel &C = s->mg[l + 1];
+            LAUNCH(s, k_mg_restrict, dim3(cdiv(C.nx, 32), cdiv(C.ny, 8)), dim3(32, 8), s->mg[l], C, s->d_sc);
+        }
+        if (lc < nlev) {
+            k_mg_coarse_cta<<<1, 1024, cta_smem, s->stream>>>(s->mg[lc], plan, s->d_sc);
+            s->launches++;
+        } else {
+            smooth(s->mg[nlev - 1], nlev == 1 ? sweeps : 16 * sweeps);
+        }
+        for (int l = top - 1; l >= 0; --l) {
+            const MgLevel &F = s->mg[l];
+            LAUNCH(s, k_mg_prolong, dim3(cdiv(F.nx, 32), cdiv(F.ny, 8)), dim3(32, 8), F, s->mg[l + 1], s->d_sc);
+            smooth(F, sweeps);
+        }
+        dim3 rgrid(cdiv(g.nx, 256), g.ny < 256 ? g.ny : 256);
+        LAUNCH(s, k_mg_residual_norm, rgrid, 256, s->mg[0], s->d_sc, s->partials, pp->tol);
+    }
+    LAUNCH(s, k_solve_finish, 1, 1, s->d_sc);
+    return 0;
+}
+
 // PressureSolver::solve, pressure.cpp:113-242.  The whole solve is enqueued; convergence is tested on the device.
 // Row slabs: every grid-level sum is completed by an allreduce + a one-thread tail kernel (identical on all ranks),
 // and the rows a neighbour's stencil reads are exchanged where the single-GPU path would simply read them.
@@ -309,8 +408,8 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
             s_new = t;
         }
     } else {
-        if (pp->mg_mode != CFD_B200_MG_REFERENCE)
-            return fail(CFD_B200_EUNSUPPORTED, "mg_mode=VCYCLE is not implemented yet");
+        if (pp->mg_mode == CFD_B200_MG_VCYCLE) return enqueue_vcycle(s, pp, s->Lx, s->Ly);
+        if (pp->mg_mode != CFD_B200_MG_REFERENCE) return fail(CFD_B200_EINVAL, "bad mg_mode %d", pp->mg_mode);
         LAUNCH(s, k_solve_begin, 1, 1, s->d_sc);
         if (s->variant != 0) { // fused smooth(): 4 colour passes + residual per launch, p ping-ponged
             const int ntx = cdiv(g.nx, RB_TX), nty = cdiv(g.ny, RB_TY);
@@ -514,6 +613,7 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
     cfd_b200_solver *s = new (std::nothrow) cfd_b200_solver;
     if (!s) return fail(CFD_B200_ENOMEM, "host allocation failed");
     s->device = device;
+    s->Lx = Lx, s->Ly = Ly;
     s->rank = rank;
     s->nranks = nranks;
     int row0 = 0, nrows = ny;
@@ -581,6 +681,10 @@ void cfd_b200_destroy(cfd_b200_solver *s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->comm) nccl_api().CommDestroy(s->comm);
+    for (int l = 1; l < s->mg_nlev; ++l) {
+        if (s->mg[l].p) cudaFree(s->mg[l].p);
+        if (s->mg[l].rhs) cudaFree(s->mg[l].rhs);
+    }
     double *fields[] = {s->u, s->v, s->p, s->p_alt, s->rhs, s->u1, s->v1, s->r, s->sA, s->sB, s->scratch_u, s->scratch_v, s->partials};
     for (double *f : fields)
         if (f) cudaFree(f);

@@ -170,6 +170,16 @@ class Lib:
     def sanitize(self, a):
         self.L.cfdo_sanitize(_ptr(a), a.size)
 
+    def vcycle_solve(self, nx, ny, Lx, Ly, p, rhs, mg_levels=3, vcycles=2, rbgs_sweeps=2, tol=1e-6):
+        """True geometric V-cycle (oracle/cfd_vcycle.c; port only -- the reference has no such code)."""
+        f = self.L.cfdo_vcycle_solve
+        f.restype = C.c_double
+        f.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double,
+                      C.POINTER(C.c_int)]
+        it = C.c_int()
+        res = f(nx, ny, Lx, Ly, _ptr(p), _ptr(rhs), mg_levels, vcycles, rbgs_sweeps, tol, C.byref(it))
+        return res, it.value
+
 
 class Sim:
     """A whole CPU simulation (Grid + State + PressureSolver + TimeIntegrator), main.cpp:104-130."""
