@@ -17,6 +17,7 @@
 #include "kernels_rhs_march.cuh"
 #include "kernels_rbgs_fused.cuh"
 #include "kernels_vcycle.cuh"
+#include "kernels_pcg_march.cuh"
 
 namespace {
 
@@ -390,14 +391,24 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
         const int ntx = cdiv(g.nx, PT_X), nty = cdiv(g.ny, PT_Y), ntiles = ntx * nty;
         const int grid = pcg_grid(s, ntiles);
         double *s_old = s->sA, *s_new = s->sB;
+        const int RY = 64; // rows per strip of the streaming kernels
+        const dim3 mgrid(cdiv(g.nx / PM_COLS + 1, PM_WARPS), cdiv(g.ny, RY));
+        const bool march = s->variant != 0;
         for (int it = 0; it < pp->pcg_max_iters; ++it) {
-            LAUNCH(s, k_pcg_phase1, grid, PT_THREADS, g, s->r, s_old, s_new, s->d_sc, s->partials, ntx, ntiles, single);
+            if (march)
+                LAUNCH(s, k_pcg_phase1_march, mgrid, 32 * PM_WARPS, g, s->r, s_old, s_new, s->d_sc, s->partials, RY, single);
+            else
+                LAUNCH(s, k_pcg_phase1, grid, PT_THREADS, g, s->r, s_old, s_new, s->d_sc, s->partials, ntx, ntiles, single);
             if (!single) {
                 TRY(allreduce(s, s->d_sc->red, 1, ncclSum));
                 LAUNCH(s, k_pcg_fin1, 1, 1, s->d_sc);
             }
-            LAUNCH(s, k_pcg_phase2, grid, PT_THREADS, g, s->p, s->r, s_new, s->d_sc, s->partials, ntx, ntiles, pp->tol,
-                   pp->pcg_max_iters, single);
+            if (march)
+                LAUNCH(s, k_pcg_phase2_march, mgrid, 32 * PM_WARPS, g, s->p, s->r, s_new, s->d_sc, s->partials, RY, pp->tol,
+                       pp->pcg_max_iters, single);
+            else
+                LAUNCH(s, k_pcg_phase2, grid, PT_THREADS, g, s->p, s->r, s_new, s->d_sc, s->partials, ntx, ntiles, pp->tol,
+                       pp->pcg_max_iters, single);
             if (!single) {
                 TRY(allreduce(s, s->d_sc->red, 2, ncclSum));
                 LAUNCH(s, k_pcg_fin2, 1, 1, s->d_sc, pp->tol, pp->pcg_max_iters);

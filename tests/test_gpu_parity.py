@@ -177,11 +177,14 @@ def test_pressure_solve_mg_bit_exact(cfd, port, nx, ny, Lx, Ly):
         assert abs(gres - ores) <= 1e-12 * ores
 
 
-@pytest.mark.parametrize("nx,ny,Lx,Ly", [(16, 16, 1.0, 1.0), (37, 21, 2.0, 0.9), (64, 32, 2.0, 1.0), (130, 67, 1.0, 1.0)])
-def test_pressure_solve_pcg(cfd, port, nx, ny, Lx, Ly):
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("nx,ny,Lx,Ly", [(16, 16, 1.0, 1.0), (37, 21, 2.0, 0.9), (64, 32, 2.0, 1.0), (130, 67, 1.0, 1.0),
+                                         (300, 211, 1.3, 0.7)])
+def test_pressure_solve_pcg(cfd, port, nx, ny, Lx, Ly, variant):
     rhs = rand_fields(nx, ny, 8)[2]
     p_junk = rand_fields(nx, ny, 9)[2]  # PCG must cold-start: junk in p (ghosts included) is cleared
     s = cfd.Solver(nx, ny, Lx, Ly)
+    s.set_variant(variant)
     for tol, cap in ((1e-6, 500), (1e-8, 25), (1e3, 50), (1e-6, 0)):
         s.upload(p=p_junk, rhs=rhs)
         op = p_junk.copy()
