@@ -184,7 +184,8 @@ void enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, const doub
         simple(0, 0, ntx, nty);
         return;
     }
-    const int RY = 64;
+    static const int ry_env = getenv("CFD_B200_RHS_RY") ? atoi(getenv("CFD_B200_RHS_RY")) : 0;
+    const int RY = ry_env > 0 ? ry_env : 64;
     dim3 mgrid(cdiv(cdiv(XB - XA + 1, MARCH_COLS), MARCH_WARPS), cdiv(YB - YA + 1, RY));
     LAUNCH(s, k_rhs_march<MODE>, mgrid, 32 * MARCH_WARPS, g, k, uin, vin, uout, vout, s->d_sc, XA, XB, YA, YB, RY);
     simple(0, 0, ntx, tyb);                    // bottom strip
@@ -278,7 +279,7 @@ void launch_fused(cfd_b200_solver *s, double tol, int ntx, int nty, int finish) 
     s->launches++;
 }
 
-// ---- EXTENSION: true geometric V-cycle (kernels_vcycle.cuh; algorithm = oracle/cfd_vcycle.c; parity unpinned) ----
+// ---- EXTENSION: true geometric V-cycle (kernels_vcycle.cuh; algorithm = the CPU restatement cfd_vcycle.c of the test tree; parity unpinned) ----
 int vcycle_levels(int nx, int ny, int mg_levels) {
     int n = 1;
     while (n < mg_levels && n < MG_CTA_MAXLEV + 3 && nx % 2 == 0 && ny % 2 == 0 && nx / 2 >= 4 && ny / 2 >= 4) nx /= 2, ny /= 2, ++n;
@@ -391,8 +392,13 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
         const int ntx = cdiv(g.nx, PT_X), nty = cdiv(g.ny, PT_Y), ntiles = ntx * nty;
         const int grid = pcg_grid(s, ntiles);
         double *s_old = s->sA, *s_new = s->sB;
-        const int RY = 64; // rows per strip of the streaming kernels
-        const dim3 mgrid(cdiv(g.nx / PM_COLS + 1, PM_WARPS), cdiv(g.ny, RY));
+        // rows per strip of the streaming kernels: tall strips amortise the 2-row prologue (8192^2: RY 64/128/256 ->
+        // 164.7/161.6/174.7 ms per 200 iterations), but keep >= 8 blocks per SM in the grid
+        static const int ry_env = getenv("CFD_B200_PCG_RY") ? atoi(getenv("CFD_B200_PCG_RY")) : 0;
+        const int gxm = cdiv(g.nx / PM_COLS + 1, PM_WARPS);
+        int RY = ry_env > 0 ? ry_env : (int)((long long)g.ny * gxm / (8 * s->sm_count));
+        if (ry_env <= 0) RY = RY > 128 ? 128 : RY < 16 ? 16 : RY;
+        const dim3 mgrid(gxm, cdiv(g.ny, RY));
         const bool march = s->variant != 0;
         for (int it = 0; it < pp->pcg_max_iters; ++it) {
             if (march)

@@ -9,8 +9,13 @@
 #pragma once
 #include "kernels_pressure.cuh"
 
+#ifndef PM_WARPS
 #define PM_WARPS 4
+#endif
 #define PM_COLS 62
+#ifndef PM_PF
+#define PM_PF 2 // rows in flight per thread (register ring); measured on B200 at 8192^2: PF 1/2/3/4 -> 170.6/164.8/175.6/178.6 ms per 200 iterations
+#endif
 
 __device__ __forceinline__ double pm_dn(double x) { return __shfl_down_sync(0xffffffffu, x, 1); }
 __device__ __forceinline__ double pm_up(double x) { return __shfl_up_sync(0xffffffffu, x, 1); }
@@ -77,22 +82,32 @@ __global__ void __launch_bounds__(32 * PM_WARPS)
         double2 s0 = direction(y0, ld(pr, y0), first ? make_double2(0.0, 0.0) : ld(ps, y0));
         if (blockIdx.y == 0) store(y0 - 1, sm1);
         store(y0, s0);
-        double2 nr = ld(pr, y0 + 1), ns = first ? make_double2(0.0, 0.0) : ld(ps, y0 + 1);
+        // register ring: rows y0+1 .. y0+PM_PF are in flight; slot k is refilled right after it is consumed
+        double2 nr[PM_PF], ns[PM_PF];
+#pragma unroll
+        for (int k = 0; k < PM_PF; ++k) {
+            nr[k] = ld(pr, min(y0 + 1 + k, g.ny + 1));
+            ns[k] = first ? make_double2(0.0, 0.0) : ld(ps, min(y0 + 1 + k, g.ny + 1));
+        }
 #pragma unroll 1
-        for (int jj = y0; jj <= y1; ++jj) {
-            const double2 sp1 = direction(jj + 1, nr, ns);
-            if (jj < y1) {
-                nr = ld(pr, jj + 2);
-                if (!first) ns = ld(ps, jj + 2);
+        for (int jb = y0; jb <= y1; jb += PM_PF) {
+#pragma unroll
+            for (int k = 0; k < PM_PF; ++k) {
+                const int jj = jb + k;
+                if (jj > y1) break;
+                const double2 sp1 = direction(jj + 1, nr[k], ns[k]);
+                const int nxt = min(jj + 1 + PM_PF, g.ny + 1); // clamped: rows past the slab are never used
+                nr[k] = ld(pr, nxt);
+                if (!first) ns[k] = ld(ps, nxt);
+                if (jj < y1 || jj + 1 == g.ny + 1) store(jj + 1, sp1); // rows of the next strip are written by that strip
+                const double left = pm_up(s0.y), right = pm_dn(s0.x);  // s(a-1, jj), s(a+2, jj)
+                const double Apa = lap5r(s0.x, left, s0.y, sm1.x, sp1.x, g.idx2, g.idy2);
+                const double Apb = lap5r(s0.y, s0.x, right, sm1.y, sp1.y, g.idx2, g.idy2);
+                if (t.out_a) acc[0] += fin0(s0.x) * fin0(Apa);
+                if (t.out_b) acc[0] += fin0(s0.y) * fin0(Apb);
+                sm1 = s0;
+                s0 = sp1;
             }
-            if (jj < y1 || jj + 1 == g.ny + 1) store(jj + 1, sp1); // rows of the next strip are written by that strip
-            const double left = pm_up(s0.y), right = pm_dn(s0.x);  // s(a-1, jj), s(a+2, jj)
-            const double Apa = lap5r(s0.x, left, s0.y, sm1.x, sp1.x, g.idx2, g.idy2);
-            const double Apb = lap5r(s0.y, s0.x, right, sm1.y, sp1.y, g.idx2, g.idy2);
-            if (t.out_a) acc[0] += fin0(s0.x) * fin0(Apa);
-            if (t.out_b) acc[0] += fin0(s0.y) * fin0(Apb);
-            sm1 = s0;
-            s0 = sp1;
         }
     }
     grid_sum<1>(acc, partials, &sc->ticket[2], [=](double(&tt)[1]) {
@@ -120,51 +135,59 @@ __global__ void __launch_bounds__(32 * PM_WARPS)
             return t.loadable ? *reinterpret_cast<const double2 *>(base + (size_t)jj * P) : make_double2(0.0, 0.0);
         };
         double2 sm1 = ld(ps, y0 - 1), s0 = ld(ps, y0); // ghost rows / columns of s are 0 in memory
-        double2 nsp = ld(ps, y0 + 1);
-        double2 np = any ? ld(pp, y0) : make_double2(0.0, 0.0), nr = any ? ld(pr, y0) : make_double2(0.0, 0.0);
+        double2 nsp[PM_PF], np[PM_PF], nr[PM_PF]; // register ring: s of rows y0+1.., p and r of rows y0..
+#pragma unroll
+        for (int k = 0; k < PM_PF; ++k) {
+            nsp[k] = ld(ps, min(y0 + 1 + k, g.ny + 1));
+            np[k] = any ? ld(pp, min(y0 + k, g.ny)) : make_double2(0.0, 0.0);
+            nr[k] = any ? ld(pr, min(y0 + k, g.ny)) : make_double2(0.0, 0.0);
+        }
 #pragma unroll 1
-        for (int jj = y0; jj <= y1; ++jj) {
-            const double2 sp1 = nsp;
-            double2 pv = np, rv = nr;
-            if (jj < y1) {
-                nsp = ld(ps, jj + 2);
+        for (int jb = y0; jb <= y1; jb += PM_PF) {
+#pragma unroll
+            for (int k = 0; k < PM_PF; ++k) {
+                const int jj = jb + k;
+                if (jj > y1) break;
+                const double2 sp1 = nsp[k];
+                double2 pv = np[k], rv = nr[k];
+                nsp[k] = ld(ps, min(jj + 1 + PM_PF, g.ny + 1));
                 if (any) {
-                    np = ld(pp, jj + 1);
-                    nr = ld(pr, jj + 1);
+                    np[k] = ld(pp, min(jj + PM_PF, g.ny));
+                    nr[k] = ld(pr, min(jj + PM_PF, g.ny));
                 }
+                const double left = pm_up(s0.y), right = pm_dn(s0.x);
+                const double Apa = lap5r(s0.x, left, s0.y, sm1.x, sp1.x, g.idx2, g.idy2);
+                const double Apb = lap5r(s0.y, s0.x, right, sm1.y, sp1.y, g.idx2, g.idy2);
+                if (t.out_a) {
+                    pv.x = pv.x + alpha * s0.x;
+                    rv.x = rv.x - alpha * Apa;
+                    if (g.j0 == 0 && jj == 1 && t.a == 1) pv.x = 0.0; // re-pin p(0,0), pressure.cpp:200
+                    if (!finite_d(pv.x)) pflag = 1;
+                    acc[0] += fin0(rv.x) * fin0(rv.x);
+                    acc[1] += fin0(rv.x) * fin0(g.inv_diag * rv.x);
+                }
+                if (t.out_b) {
+                    pv.y = pv.y + alpha * s0.y;
+                    rv.y = rv.y - alpha * Apb;
+                    if (g.j0 == 0 && jj == 1 && t.a + 1 == 1) pv.y = 0.0;
+                    if (!finite_d(pv.y)) pflag = 1;
+                    acc[0] += fin0(rv.y) * fin0(rv.y);
+                    acc[1] += fin0(rv.y) * fin0(g.inv_diag * rv.y);
+                }
+                const size_t o = (size_t)jj * P;
+                if (t.out_a && t.out_b) {
+                    *reinterpret_cast<double2 *>(pp + o) = pv;
+                    *reinterpret_cast<double2 *>(pr + o) = rv;
+                } else if (t.out_a) {
+                    pp[o] = pv.x;
+                    pr[o] = rv.x;
+                } else if (t.out_b) {
+                    pp[o + 1] = pv.y;
+                    pr[o + 1] = rv.y;
+                }
+                sm1 = s0;
+                s0 = sp1;
             }
-            const double left = pm_up(s0.y), right = pm_dn(s0.x);
-            const double Apa = lap5r(s0.x, left, s0.y, sm1.x, sp1.x, g.idx2, g.idy2);
-            const double Apb = lap5r(s0.y, s0.x, right, sm1.y, sp1.y, g.idx2, g.idy2);
-            if (t.out_a) {
-                pv.x = pv.x + alpha * s0.x;
-                rv.x = rv.x - alpha * Apa;
-                if (g.j0 == 0 && jj == 1 && t.a == 1) pv.x = 0.0; // re-pin p(0,0), pressure.cpp:200
-                if (!finite_d(pv.x)) pflag = 1;
-                acc[0] += fin0(rv.x) * fin0(rv.x);
-                acc[1] += fin0(rv.x) * fin0(g.inv_diag * rv.x);
-            }
-            if (t.out_b) {
-                pv.y = pv.y + alpha * s0.y;
-                rv.y = rv.y - alpha * Apb;
-                if (g.j0 == 0 && jj == 1 && t.a + 1 == 1) pv.y = 0.0;
-                if (!finite_d(pv.y)) pflag = 1;
-                acc[0] += fin0(rv.y) * fin0(rv.y);
-                acc[1] += fin0(rv.y) * fin0(g.inv_diag * rv.y);
-            }
-            const size_t o = (size_t)jj * P;
-            if (t.out_a && t.out_b) {
-                *reinterpret_cast<double2 *>(pp + o) = pv;
-                *reinterpret_cast<double2 *>(pr + o) = rv;
-            } else if (t.out_a) {
-                pp[o] = pv.x;
-                pr[o] = rv.x;
-            } else if (t.out_b) {
-                pp[o + 1] = pv.y;
-                pr[o + 1] = rv.y;
-            }
-            sm1 = s0;
-            s0 = sp1;
         }
     }
     if (pflag) sc->nonfinite_p = 1;

@@ -25,6 +25,11 @@
 #include "kernels_step.cuh"
 
 #define MARCH_WARPS 4
+#ifndef MARCH_UNROLL
+#define MARCH_UNROLL 3 // B200, 8192^2: unroll 1/2/3/4 -> stage 1 0.555/0.558/0.542/0.614 ms (3 = period of the q rotation)
+#endif
+#define MARCH_STR2(x) #x
+#define MARCH_STR(x) MARCH_STR2(x)
 #ifndef MARCH_MINBLOCKS
 #define MARCH_MINBLOCKS 4 // resident blocks per SM the register allocator must allow (tuned on B200, see profiles/)
 #endif
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS, MARCH_MINBLOCKS)
 
     // rows are requested one iteration ahead of their use (ncu: the loop was stalled on its own loads)
     double2 pre_u = ld2(pu, y0 + 2), pre_v = ld2(pv, y0 + 2);
-#pragma unroll 1
+_Pragma(MARCH_STR(unroll MARCH_UNROLL))
     for (int jj = y0; jj <= y1; ++jj) {
         const double2 nu = pre_u, nv = pre_v;
         if (jj < y1) {

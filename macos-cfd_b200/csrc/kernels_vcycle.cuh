@@ -1,6 +1,6 @@
 // kernels_vcycle.cuh -- EXTENSION: a true geometric V-cycle (mg_mode = CFD_B200_MG_VCYCLE) honouring mg_levels and
 // rbgs_sweeps.  The reference has no multigrid (its "Multigrid" is fine-grid RBGS, pressure.cpp:113-129), so this
-// mode has NO reference oracle: parity is UNPINNED.  The algorithm is defined by oracle/cfd_vcycle.c and these
+// mode has NO reference oracle: parity is UNPINNED.  The algorithm is defined by the CPU restatement cfd_vcycle.c (test tree) and these
 // kernels reproduce it bit for bit (same expressions, IEEE division, no FMA); see that file for the method:
 // cell-centred coarsening by 2, red-black Gauss-Seidel with the correct sign, p = 0 on the wall faces (modified
 // diagonal for wall cells: the same physical boundary on every level), residual + 4-cell-mean restriction fused,
