@@ -169,9 +169,15 @@ void enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, const doub
     RhsConst k{g.idx, g.idy, g.idx2, g.idy2, invRe};
     const dim3 block(RHS_TX, RHS_TY);
     const int ntx = cdiv(g.nx + 1, RHS_TX), nty = cdiv(g.ny + 1, RHS_TY);
-    auto simple = [&](int tx0, int ty0, int ntx_, int nty_) {
-        if (ntx_ > 0 && nty_ > 0)
-            LAUNCH(s, k_rhs_simple<MODE>, dim3(ntx_, nty_), block, g, k, uin, vin, uout, vout, s->d_sc, tx0, ty0);
+    RhsRects rc{};
+    auto add = [&](int tx0, int ty0, int ntx_, int nty_) {
+        if (ntx_ <= 0 || nty_ <= 0) return;
+        const int k = rc.n++;
+        rc.tx0[k] = tx0, rc.ty0[k] = ty0, rc.ntx[k] = ntx_;
+        rc.end[k] = (k ? rc.end[k - 1] : 0) + ntx_ * nty_;
+    };
+    auto launch_rects = [&]() {
+        if (rc.n > 0) LAUNCH(s, k_rhs_simple<MODE>, rc.end[rc.n - 1], block, g, k, uin, vin, uout, vout, s->d_sc, rc);
     };
     // Interior faces (all four fluxes MUSCL, for u and v alike): 2 <= ii <= nx-1, 2 <= jj <= ny-1.  The marching kernel
     // takes the part of it that is aligned to the simple kernel's tiles; the tile strips around it (ring included)
@@ -181,17 +187,19 @@ void enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, const doub
     const int tyt = g.top ? (g.ny - 1) / RHS_TY : nty;          // first tile row of the top strip
     const int XA = RHS_TX + 1, XB = txr * RHS_TX, YA = tyb * RHS_TY + 1, YB = g.top ? tyt * RHS_TY : g.ny;
     if (s->variant == 0 || XB < XA + 16 || YB < YA + 8) {
-        simple(0, 0, ntx, nty);
+        add(0, 0, ntx, nty);
+        launch_rects();
         return;
     }
     static const int ry_env = getenv("CFD_B200_RHS_RY") ? atoi(getenv("CFD_B200_RHS_RY")) : 0;
     const int RY = ry_env > 0 ? ry_env : 64;
     dim3 mgrid(cdiv(cdiv(XB - XA + 1, MARCH_COLS), MARCH_WARPS), cdiv(YB - YA + 1, RY));
     LAUNCH(s, k_rhs_march<MODE>, mgrid, 32 * MARCH_WARPS, g, k, uin, vin, uout, vout, s->d_sc, XA, XB, YA, YB, RY);
-    simple(0, 0, ntx, tyb);                    // bottom strip
-    simple(0, tyt, ntx, nty - tyt);            // top strip
-    simple(0, tyb, 1, tyt - tyb);              // left strip
-    simple(txr, tyb, ntx - txr, tyt - tyb);    // right strip
+    add(0, 0, ntx, tyb);                    // bottom strip
+    add(0, tyt, ntx, nty - tyt);            // top strip
+    add(0, tyb, 1, tyt - tyb);              // left strip
+    add(txr, tyb, ntx - txr, tyt - tyb);    // right strip
+    launch_rects();                         // one launch for all four
 }
 
 dim3 row_grid(const cfd_b200_solver *s, int ncols, int nrows, int *rows_per_block) {
@@ -392,14 +400,17 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
         const int ntx = cdiv(g.nx, PT_X), nty = cdiv(g.ny, PT_Y), ntiles = ntx * nty;
         const int grid = pcg_grid(s, ntiles);
         double *s_old = s->sA, *s_new = s->sB;
-        // rows per strip of the streaming kernels: tall strips amortise the 2-row prologue (8192^2: RY 64/128/256 ->
-        // 164.7/161.6/174.7 ms per 200 iterations), but keep >= 8 blocks per SM in the grid
+        // Streaming kernels for grids that fill the GPU, tile kernels below that (B200: 512x256 tile 3.1 ms vs streaming
+        // 4.1 ms per step; 4096^2 tile 49.9 vs streaming 46.4; 8192^2 187 vs 162).  Rows per strip: a power of two
+        // (4096^2: RY 32/58/64/128 -> 46.4/52.2/47.0/52.2 ms; 8192^2: 64/128/256 -> 164.7/161.6/174.7) that leaves
+        // >= 8 blocks per SM in the grid.
         static const int ry_env = getenv("CFD_B200_PCG_RY") ? atoi(getenv("CFD_B200_PCG_RY")) : 0;
         const int gxm = cdiv(g.nx / PM_COLS + 1, PM_WARPS);
-        int RY = ry_env > 0 ? ry_env : (int)((long long)g.ny * gxm / (8 * s->sm_count));
-        if (ry_env <= 0) RY = RY > 128 ? 128 : RY < 16 ? 16 : RY;
+        int RY = 8;
+        while (RY < 128 && (long long)g.ny * gxm / (2 * RY) >= 8LL * s->sm_count) RY *= 2;
+        if (ry_env > 0) RY = ry_env;
         const dim3 mgrid(gxm, cdiv(g.ny, RY));
-        const bool march = s->variant != 0;
+        const bool march = s->variant != 0 && (ry_env > 0 || (long long)g.nx * g.ny >= (2LL << 20));
         for (int it = 0; it < pp->pcg_max_iters; ++it) {
             if (march)
                 LAUNCH(s, k_pcg_phase1_march, mgrid, 32 * PM_WARPS, g, s->r, s_old, s_new, s->d_sc, s->partials, RY, single);
@@ -870,8 +881,10 @@ int cfd_b200_advect(cfd_b200_solver *s, double *du, double *dv) {
     CU(cudaMemsetAsync(s->scratch_u, 0, s->n * sizeof(double), s->stream)); // advect_* zero-fill first (advection.cpp:41)
     CU(cudaMemsetAsync(s->scratch_v, 0, s->n * sizeof(double), s->stream));
     RhsConst k{g.idx, g.idy, g.idx2, g.idy2, 0.0};
-    dim3 grid(cdiv(g.nx + 1, RHS_TX), cdiv(g.ny + 1, RHS_TY)), block(RHS_TX, RHS_TY);
-    LAUNCH(s, k_rhs_simple<3>, grid, block, g, k, s->u, s->v, s->scratch_u, s->scratch_v, s->d_sc, 0, 0);
+    dim3 block(RHS_TX, RHS_TY);
+    RhsRects rects{};
+    rects.n = 1, rects.ntx[0] = cdiv(g.nx + 1, RHS_TX), rects.end[0] = rects.ntx[0] * cdiv(g.ny + 1, RHS_TY);
+    LAUNCH(s, k_rhs_simple<3>, rects.end[0], block, g, k, s->u, s->v, s->scratch_u, s->scratch_v, s->d_sc, rects);
     if (du && (rc = copy_field(s, s->scratch_u, du, g.nx + 3, g.ny + 2, false))) return rc;
     if (dv && (rc = copy_field(s, s->scratch_v, dv, g.nx + 2, g.ny + 3, false))) return rc;
     CU(cudaStreamSynchronize(s->stream));

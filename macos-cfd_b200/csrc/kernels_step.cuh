@@ -281,13 +281,22 @@ __device__ __forceinline__ double rhs_point(const double *qc, const double *uc, 
 // MODE 3: advect_u / advect_v as free functions: the advective derivative only, not sanitised
 #define RHS_TX 32
 #define RHS_TY 8
+// Up to four rectangles of tiles handled by ONE launch (the strips around the marching kernel's region): a linear block
+// index is mapped to (rectangle, tile) through the running tile counts.
+struct RhsRects {
+    int n;
+    int tx0[4], ty0[4], ntx[4], end[4]; // end[k] = number of tiles in rectangles 0..k
+};
 template <int MODE>
 __global__ void __launch_bounds__(RHS_TX *RHS_TY)
     k_rhs_simple(Geom g, RhsConst k, const double *__restrict__ uin, const double *__restrict__ vin, double *uout,
-                 double *vout, Scalars *sc, int tx0, int ty0) {
+                 double *vout, Scalars *sc, RhsRects rc) {
     constexpr int S = RHS_TX + 4 + 1; // +1: odd stride
     __shared__ double us[(RHS_TY + 4) * S], vs[(RHS_TY + 4) * S];
-    const int x0 = 1 + (tx0 + blockIdx.x) * RHS_TX, y0 = 1 + (ty0 + blockIdx.y) * RHS_TY; // tile offset: strips
+    int rk = 0, first = 0;
+    while (rk < rc.n - 1 && (int)blockIdx.x >= rc.end[rk]) first = rc.end[rk], ++rk;
+    const int t = blockIdx.x - first, tyr = t / rc.ntx[rk], txr = t - tyr * rc.ntx[rk];
+    const int x0 = 1 + (rc.tx0[rk] + txr) * RHS_TX, y0 = 1 + (rc.ty0[rk] + tyr) * RHS_TY;
     const int tid = threadIdx.y * RHS_TX + threadIdx.x;
     const int max_col = g.P - CFD_XOFF - 1, max_row = g.rows - CFD_YOFF - 1;
     for (int t = tid; t < (RHS_TY + 4) * (RHS_TX + 4); t += RHS_TX * RHS_TY) {
