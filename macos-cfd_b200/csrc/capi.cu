@@ -70,6 +70,8 @@ struct cfd_b200_solver {
     bool ev_valid = false;
     int sm_count = 148;
     ncclComm_t comm = nullptr; // row slabs only
+    double *gathered = nullptr; // 4 doubles per rank (k_slab_pack / k_slab_unpack)
+    bool halo_uv_valid = false; // the 2 halo rows of u, v are current (set by the exchange that ends a step)
     // V-cycle extension: coarse levels (level 0 aliases p / rhs), allocated on first use
     int mg_nlev = 0;
     MgLevel mg[MG_CTA_MAXLEV + 4] = {};
@@ -143,7 +145,7 @@ void stage_mark(cfd_b200_solver *s, int st) {
 // apply_bc_u / apply_bc_v / apply_bc_p in the reference's pass order (left/right, then bottom/top)
 void enqueue_bc(cfd_b200_solver *s, const BcD &bc, double *u, double *v, double *p, int sanitize) {
     const Geom &g = s->g;
-    LAUNCH(s, k_bc_lr, cdiv(g.ny + 1, 128), 128, g, bc, u, v, p, sanitize, s->d_sc);
+    LAUNCH(s, k_bc_lr, cdiv(g.ny + 5, 128), 128, g, bc, u, v, p, sanitize, s->d_sc);
     if (g.bottom || g.top) LAUNCH(s, k_bc_bt, cdiv(g.nx + 3, 128), 128, g, bc, u, v, p, sanitize, s->d_sc);
 }
 
@@ -156,10 +158,10 @@ void enqueue_cfl(cfd_b200_solver *s, double Re, double CFL, double dt_override, 
         cudaMemsetAsync(&s->d_sc->umax_bits, 0, 2 * sizeof(unsigned long long), s->stream);
         dim3 grid(cdiv(g.P / 2, 256), g.ny + 1 < 64 ? g.ny + 1 : 64);
         LAUNCH(s, k_absmax, grid, 256, g, s->u, s->v, s->d_sc);
+        // non-negative doubles order like their bit patterns, so the maxima can be all-reduced as doubles
+        if (s->nranks > 1) nccl_api().AllReduce(&s->d_sc->umax_bits, &s->d_sc->umax_bits, 2, ncclDouble, ncclMax, s->comm, s->stream);
     }
     s->cfl_cached = false;
-    // non-negative doubles order like their bit patterns, so the maxima can be all-reduced as doubles
-    if (s->nranks > 1) nccl_api().AllReduce(&s->d_sc->umax_bits, &s->d_sc->umax_bits, 2, ncclDouble, ncclMax, s->comm, s->stream);
     LAUNCH(s, k_dt, 1, 1, g, Re, CFL, dt_override, s->d_sc, cfl_only);
 }
 
@@ -441,9 +443,9 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
         LAUNCH(s, k_solve_begin, 1, 1, s->d_sc);
         if (s->variant != 0) { // fused smooth(): 4 colour passes + residual per launch, p ping-ponged
             const int ntx = cdiv(g.nx, RB_TX), nty = cdiv(g.ny, RB_TY);
-            if (!single) TRY(halo_exchange2(s, s->rhs, nullptr, RB_HY, HALO_BOTH)); // rhs is constant during the solve
             for (int vc = 0; vc < pp->vcycles; ++vc) {
-                if (!single) TRY(halo_exchange2(s, s->p, nullptr, RB_HY, HALO_BOTH)); // 5 rows: redundant compute
+                // 5 rows of p (and, once, of rhs: it is constant during the solve) for the redundant compute
+                if (!single) TRY(halo_exchange2(s, s->p, vc == 0 ? s->rhs : nullptr, RB_HY, HALO_BOTH));
                 if (g.denom_pow2) launch_fused<1>(s, pp->tol, ntx, nty, single);
                 else launch_fused<0>(s, pp->tol, ntx, nty, single);
                 if (!single) {
@@ -496,11 +498,12 @@ int enqueue_step(cfd_b200_solver *s, const cfd_b200_bc *bc_in, double Re, double
     if (both_bt && s->nranks > 1)
         return fail(CFD_B200_EUNSUPPORTED, "bottom/top Periodic is not supported across row slabs");
     const double invRe = 1.0 / Re; // "1.0 / Re" at time_integrator.cpp:76
-    if (!bc_equal(s->last_bc, *bc_in) || s->variant == 0 || s->nranks > 1) s->cfl_cached = false;
+    if (!bc_equal(s->last_bc, *bc_in) || s->variant == 0) s->cfl_cached = false;
     s->last_bc = *bc_in;
     stage_mark(s, ST_BC0);
     enqueue_bc(s, bc, s->u, s->v, s->p, 0); // :51-53
-    TRY(halo_exchange2(s, s->u, s->v, 2, HALO_BOTH)); // the advection stencil reads 2 rows beyond the slab
+    // the advection stencil reads 2 rows beyond the slab; they are current unless the State was uploaded since
+    if (!s->halo_uv_valid) TRY(halo_exchange2(s, s->u, s->v, 2, HALO_BOTH));
     stage_mark(s, ST_CFL);
     enqueue_cfl(s, Re, CFL, dt_override, 0); // :55-66
     stage_mark(s, ST_RHS1);
@@ -523,11 +526,16 @@ int enqueue_step(cfd_b200_solver *s, const cfd_b200_bc *bc_in, double Re, double
     enqueue_project(s, s->d_sc, 0.0); // :188-202
     stage_mark(s, ST_BC3);
     enqueue_bc(s, bc, s->u, s->v, s->p, 1); // :205-207
-    TRY(halo_exchange2(s, s->v, nullptr, 1, HALO_DOWN));
+    TRY(halo_exchange2(s, s->u, s->v, 2, HALO_BOTH)); // v row above for the divergence; everything else for the next step
+    s->halo_uv_valid = s->nranks > 1;
     stage_mark(s, ST_DIV2);
     enqueue_divergence(s, 0, 1, 1); // :210-220 (+ max|u|, max|v| for the next step's compute_cfl)
     s->cfl_cached = true;
-    TRY(allreduce(s, &s->d_sc->div_before, 2, ncclSum)); // slabs hold partial sums of squares here
+    if (s->nranks > 1) { // one collective: CFL maxima of the next step + the two partial sums of squares
+        LAUNCH(s, k_slab_pack, 1, 1, s->d_sc);
+        NCCLCHK(nccl_api().AllGather(s->d_sc->red, s->gathered, 4, ncclDouble, s->comm, s->stream));
+        LAUNCH(s, k_slab_unpack, 1, 1, s->d_sc, s->gathered, s->nranks);
+    }
     LAUNCH(s, k_sanitize_if, s->sm_count * 4, 256, g, s->p, s->d_sc); // :236
     stage_mark(s, ST_END);
     s->ev_valid = s->profiling != 0;
@@ -683,6 +691,7 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
             memcpy(&id, nccl_id128, sizeof(id));
             ncclResult_t r = nccl_api().CommInitRank(&s->comm, nranks, id, rank);
             if (r != ncclSuccess) { rc = fail(CFD_B200_ECOMM, "ncclCommInitRank: %s", nccl_api().GetErrorString(r)); break; }
+            if (cudaMalloc(&s->gathered, 4 * nranks * sizeof(double)) != cudaSuccess) { rc = fail(CFD_B200_ENOMEM, "gather buffer"); break; }
         }
     } while (0);
     if (rc) {
@@ -709,6 +718,7 @@ void cfd_b200_destroy(cfd_b200_solver *s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->comm) nccl_api().CommDestroy(s->comm);
+    if (s->gathered) cudaFree(s->gathered);
     for (int l = 1; l < s->mg_nlev; ++l) {
         if (s->mg[l].p) cudaFree(s->mg[l].p);
         if (s->mg[l].rhs) cudaFree(s->mg[l].rhs);
@@ -729,7 +739,7 @@ int cfd_b200_upload(cfd_b200_solver *s, const double *u, const double *v, const 
     CU(cudaSetDevice(s->device));
     const Geom &g = s->g;
     int rc = 0;
-    if (u || v) s->cfl_cached = false;
+    if (u || v) s->cfl_cached = false, s->halo_uv_valid = false;
     if (u && (rc = copy_field(s, s->u, const_cast<double *>(u), g.nx + 3, g.ny + 2, true))) return rc;
     if (v && (rc = copy_field(s, s->v, const_cast<double *>(v), g.nx + 2, g.ny + 3, true))) return rc;
     if (p && (rc = copy_field(s, s->p, const_cast<double *>(p), g.nx + 2, g.ny + 2, true))) return rc;
@@ -837,7 +847,7 @@ int cfd_b200_max_velocity(cfd_b200_solver *s, double *out) {
 int cfd_b200_apply_bc(cfd_b200_solver *s, const cfd_b200_bc *bc, int which) {
     if (!s || !bc) return fail(CFD_B200_EINVAL, "NULL argument");
     CU(cudaSetDevice(s->device));
-    s->cfl_cached = false;
+    s->cfl_cached = false, s->halo_uv_valid = false;
     enqueue_bc(s, to_bcd(bc), (which & 1) ? s->u : nullptr, (which & 2) ? s->v : nullptr, (which & 4) ? s->p : nullptr, 0);
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
@@ -936,7 +946,7 @@ int cfd_b200_pressure_solve(cfd_b200_solver *s, const cfd_b200_params *pp, doubl
 int cfd_b200_subtract_grad_p(cfd_b200_solver *s, double dt) {
     if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
     CU(cudaSetDevice(s->device));
-    s->cfl_cached = false;
+    s->cfl_cached = false, s->halo_uv_valid = false;
     enqueue_project(s, nullptr, dt, 0);
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());

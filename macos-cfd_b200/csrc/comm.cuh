@@ -25,6 +25,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -54,6 +55,7 @@ struct NcclApi {
         NCCL_SYM(CommInitRank, "ncclCommInitRank")
         NCCL_SYM(CommDestroy, "ncclCommDestroy")
         NCCL_SYM(AllReduce, "ncclAllReduce")
+        NCCL_SYM(AllGather, "ncclAllGather")
         NCCL_SYM(Send, "ncclSend")
         NCCL_SYM(Recv, "ncclRecv")
         NCCL_SYM(GroupStart, "ncclGroupStart")

@@ -55,20 +55,23 @@ __device__ __forceinline__ void bc_row(double *row, int cR, bool both, int ltype
     }
 }
 
+// Row slabs: the pass also covers the 2 halo rows towards a neighbouring slab.  It is row-local, so this reproduces
+// exactly what the neighbour does to its own rows and the halo rows stay current without an exchange.
 __global__ void k_bc_lr(Geom g, BcD bc, double *u, double *v, double *p, int sanitize, Scalars *sc) {
-    int jj = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int jlo = g.bottom ? 1 : -1;
+    int jj = blockIdx.x * blockDim.x + threadIdx.x + jlo;
     int flag = 0;
     bool both = bc.left.type == BC_PERIODIC && bc.right.type == BC_PERIODIC;
-    if (u && jj <= g.ny) { // apply_bc_u rows, bc.cpp:38-107: u is the normal component here
+    if (u && jj <= (g.top ? g.ny : g.ny + 2)) { // apply_bc_u rows, bc.cpp:38-107: u is the normal component here
         double y = ((g.j0 + jj - 1) + 0.5) * g.dy;
         bc_row(u + gidx(g, 0, jj), g.nx + 1, both, bc.left.type, 0.0, jet_profile(bc, y), bc.right.type, 0.0,
                bc.right.inflow_u, sanitize, flag);
     }
-    if (v && jj <= v_rows(g)) { // apply_bc_v rows, bc.cpp:192-264: tangential; left Inflow gives 0
+    if (v && jj <= (g.top ? g.ny + 1 : g.ny + 2)) { // apply_bc_v rows, bc.cpp:192-264: tangential; left Inflow gives 0
         bc_row(v + gidx(g, 0, jj), g.nx, both, bc.left.type, bc.left.moving, 0.0, bc.right.type,
                bc.right.moving, bc.right.inflow_v, sanitize, flag);
     }
-    if (p && jj <= g.ny) { // apply_bc_p rows, bc.cpp:340-358
+    if (p && jj >= 1 && jj <= g.ny) { // apply_bc_p rows, bc.cpp:340-358
         double *row = p + gidx(g, 0, jj);
         if (sanitize) {
             row[0] = sanitize_val(row[0], flag);
@@ -459,6 +462,27 @@ __global__ void __launch_bounds__(256)
         pb = pc;
     }
     if (flag) flags->nonfinite_any = 1;
+}
+
+// Row slabs, end of a step: one all-gather carries what compute_cfl of the NEXT step and the divergence log need.
+__global__ void k_slab_pack(Scalars *sc) {
+    sc->red[0] = __longlong_as_double((long long)sc->umax_bits);
+    sc->red[1] = __longlong_as_double((long long)sc->vmax_bits);
+    sc->red[2] = sc->div_before; // partial sums of squares
+    sc->red[3] = sc->div_after;
+}
+__global__ void k_slab_unpack(Scalars *sc, const double *gathered, int nranks) {
+    double um = 0.0, vm = 0.0, db = 0.0, da = 0.0;
+    for (int r = 0; r < nranks; ++r) { // fixed rank order: identical on every rank
+        um = max2(um, gathered[4 * r]);
+        vm = max2(vm, gathered[4 * r + 1]);
+        db += gathered[4 * r + 2];
+        da += gathered[4 * r + 3];
+    }
+    sc->umax_bits = (unsigned long long)__double_as_longlong(um);
+    sc->vmax_bits = (unsigned long long)__double_as_longlong(vm);
+    sc->div_before = db;
+    sc->div_after = da;
 }
 
 // sanitize_field(s.p) (time_integrator.cpp:236); only does work when the solver flagged a non-finite p
