@@ -38,6 +38,8 @@ WORKLOADS = {
     "shear_pcg_4096": ("shear", "pcg", 4096, 4096, 1.0, 1.0, 2, 1e-6, 200, 2),
     "jet_mg_1024": ("jet", "mg", 1024, 1024, 1.0, 1.0, 2, 1e-6, 200, 1),
     "lid_pcg_512x256": ("lid", "pcg", 512, 256, 2.0, 1.0, 2, 1e-8, 200, 0),
+    # BASELINE configs[3]: STRONG scaling -- the 8192^2 grid is fixed and split into N row slabs
+    "lid_mg_8192_strong": ("lid", "mg", 8192, 8192, 1.0, 1.0, 2, 1e-6, 200, 3),
 }
 DEFAULT_WORKLOAD = "jet_mg_8192"
 
@@ -51,8 +53,9 @@ SURVEY_STEP_BYTES = {"mg": lambda vcycles, iters: 184 + 64 * vcycles, "pcg": lam
 STAGE_KERNEL = {"rhs_stage1": "k_rhs_march<1>", "rhs_stage2": "k_rhs_march<2>", "divergence": "k_divergence<1>",
                 "project": "k_project", "divergence_post": "k_divergence<0>"}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/r01_*), 8192 x 8192 only
-NCU_TRAFFIC_8192 = {"k_rbgs_fused": 1.079e9 + 0.505e9, "k_rhs_march<1>": 1.138e9 + 1.022e9,
-                    "k_rhs_march<2>": 2.200e9 + 1.023e9, "k_project": 1.623e9 + 1.023e9,
+NCU_TRAFFIC_8192 = {"k_rbgs_fused": 1.0816e9 + 0.5221e9, "k_rhs_march<1>": 1.1385e9 + 1.0216e9,
+                    "k_rhs_march<2>": 2.1998e9 + 1.0244e9, "k_project": 1.6301e9 + 1.0227e9,
+                    "k_divergence<1>": 1.0831e9 + 0.5114e9, "k_divergence<0>": 1.0832e9 + 0.5101e9,
                     "k_pcg_phase1_march + k_pcg_phase2_march (one iteration)": 1.112e9 + 0.510e9 + 1.629e9 + 1.022e9}
 
 
@@ -156,14 +159,19 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     N = args.gpus
-    ny, Ly = ny_gpu * N, Ly_gpu * N  # weak scaling: row slabs stacked in y
+    strong = args.workload.endswith("_strong")
+    if strong:
+        ny, Ly = ny_gpu, Ly_gpu          # strong scaling: the global grid is fixed
+        ny_gpu = ny // N
+    else:
+        ny, Ly = ny_gpu * N, Ly_gpu * N  # weak scaling: row slabs stacked in y
     config = {"workload": args.workload, "baseline_config": cfg_idx, "preset": preset, "solver": solver,
               "grid": f"{nx}x{ny}", "domain": f"{Lx}x{Ly}", "vcycles": vcycles, "tol": tol, "pcg_max_iters": iters,
               "decomposition": f"{N} row slab(s) of {nx}x{ny_gpu}",
               "l2": "fields (>= 0.5 GB each) exceed the 126 MB L2" if nx * ny_gpu * 8 > 200e6 else
               "L2 flushed (256 MB write) before every timed step"}
     base = {"metric": "cell-updates/s (full timestep incl. Poisson)", "unit": "cell-updates/s", "n_gpus": N,
-            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic (deterministic preset initial/boundary data)",
             "config": config}
 
