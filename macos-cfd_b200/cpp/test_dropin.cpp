@@ -1,0 +1,86 @@
+// test_dropin.cpp -- exercises the reference-shaped C++ layer the way the reference's GUI loop does (main.cpp:200-264):
+// eager coherence (the host State is current after every step), a host-side write between steps (what
+// apply_shapes_to_simulation does, main.cpp:246), dt_override (gui.dt), and the public free functions.  It writes raw
+// dumps that tests/test_gpu_cpp_driver.py compares with the oracle.   usage: test_dropin <outdir>
+#include <cstdio>
+#include <fstream>
+#include <string>
+
+#include "b200_backend.hpp"
+#include "solver/time_integrator.hpp"
+
+static void dump(const std::string &path, const Field2D<double> &f) {
+    std::ofstream out(path, std::ios::binary);
+    out.write(reinterpret_cast<const char *>(f.data), static_cast<std::streamsize>(f.count() * sizeof(double)));
+}
+
+int main(int argc, char **argv) {
+    if (argc < 2) return 2;
+    const std::string dir = argv[1];
+    try {
+        b200::set_coherence(b200::Coherence::Eager);
+        Grid grid;
+        grid.init(72, 40, 1.8, 1.0, 1);
+        State st;
+        st.u.allocate(grid.u_nx(), grid.ny, grid.u_pitch(), grid.ngx, grid.ngy);
+        st.v.allocate(grid.nx, grid.v_ny(), grid.v_pitch(), grid.ngx, grid.ngy);
+        st.p.allocate(grid.nx, grid.ny, grid.p_pitch(), grid.ngx, grid.ngy);
+        st.rhs.allocate(grid.nx, grid.ny, grid.p_pitch(), grid.ngx, grid.ngy);
+        PressureSolver pressure(grid);
+        TimeIntegrator integ(grid);
+        integ.clear_work();
+        BC bc; // lid-driven cavity preset, main.cpp:288-296
+        bc.left.type = bc.right.type = bc.bottom.type = BCType::Wall;
+        bc.top.type = BCType::Moving;
+        bc.top.moving = 1.0;
+        PressureParams pp;
+        pp.type = PressureSolverType::Multigrid;
+        pp.vcycles = 2;
+        double res = 0.0;
+        std::ofstream log(dir + "/log.txt");
+        log.precision(17);
+        for (int step = 0; step < 6; ++step) {
+            double dt = integ.step(st, bc, 1000.0, 0.1, pressure, pp, res, /*dt_override=*/0.0005);
+            // the host State is current (eager): diagnostics and a GUI-style obstacle edit work on plain host arrays
+            double d = divergence_l2(grid, st.u, st.v), m = max_velocity(grid, st.u, st.v);
+            log << dt << ' ' << res << ' ' << d << ' ' << m << "\n";
+            for (int jj = 10; jj < 14; ++jj) // "porous" obstacle: u *= 0.1 inside a small box (shapes.cpp:40-60)
+                for (int ii = 20; ii < 26; ++ii) st.u.at_raw(ii, jj) *= 0.1;
+        }
+        dump(dir + "/u.bin", st.u), dump(dir + "/v.bin", st.v), dump(dir + "/p.bin", st.p), dump(dir + "/rhs.bin", st.rhs);
+
+        // free functions on caller arrays
+        Field2D<double> u2, v2, p2, du, rhs2;
+        u2.allocate(grid.u_nx(), grid.ny, grid.u_pitch(), 1, 1);
+        du.allocate(grid.u_nx(), grid.ny, grid.u_pitch(), 1, 1);
+        v2.allocate(grid.nx, grid.v_ny(), grid.v_pitch(), 1, 1);
+        p2.allocate(grid.nx, grid.ny, grid.p_pitch(), 1, 1);
+        rhs2.allocate(grid.nx, grid.ny, grid.p_pitch(), 1, 1);
+        for (size_t i = 0; i < u2.count(); ++i) u2.data[i] = st.u.data[i];
+        for (size_t i = 0; i < v2.count(); ++i) v2.data[i] = st.v.data[i];
+        for (size_t i = 0; i < p2.count(); ++i) p2.data[i] = st.p.data[i];
+        BC jet;
+        jet.left.type = BCType::Inflow, jet.right.type = BCType::Outflow;
+        jet.jet_center = 0.5, jet.jet_width = 0.18;
+        apply_bc_u(grid, u2, jet);
+        apply_bc_v(grid, v2, jet);
+        apply_bc_p(grid, p2, jet);
+        log << compute_cfl(grid, u2, v2, 50.0, 0.01) << "\n";
+        advect_u(grid, u2, v2, du);
+        diffuse_u(grid, u2, du, 1.0 / 50.0);
+        divergence(grid, u2, v2, rhs2);
+        subtract_grad_p(grid, u2, v2, p2, 1e-3);
+        PressureParams pcg;
+        pcg.type = PressureSolverType::PCG;
+        pcg.pcg_max_iters = 30;
+        pcg.tol = 1e-9;
+        PressureSolver solver2(grid);
+        log << solver2.solve(p2, rhs2, pcg) << ' ' << solver2.last_iterations() << "\n";
+        dump(dir + "/f_u.bin", u2), dump(dir + "/f_v.bin", v2), dump(dir + "/f_p.bin", p2), dump(dir + "/f_du.bin", du),
+            dump(dir + "/f_rhs.bin", rhs2);
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "test_dropin: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

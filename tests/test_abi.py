@@ -71,3 +71,19 @@ def test_no_fma_in_device_code():
         assert blocks, kern
         for b in blocks:
             assert "DFMA" not in b, kern
+
+
+def test_argument_validation_happens_before_the_device_is_touched():
+    """Bad arguments are CFD_B200_EINVAL (-1) even on a box without a GPU; errors carry a message."""
+    import ctypes as C
+    m = importlib.import_module("macos-cfd_b200")
+    L = m.load_library()
+    h = C.c_void_p()
+    for nx, ny, Lx, Ly in ((3, 16, 1.0, 1.0), (16, 2, 1.0, 1.0), (16, 16, 0.0, 1.0), (16, 16, 1.0, -1.0)):
+        assert L.cfd_b200_create(nx, ny, Lx, Ly, 0, C.byref(h)) == -1
+        assert L.cfd_b200_last_error()
+    assert L.cfd_b200_create(16, 16, 1.0, 1.0, 0, None) == -1
+    assert L.cfd_b200_create_slab(64, 64, 1.0, 1.0, 0, 3, 2, None, C.byref(h)) == -1   # rank out of range
+    assert L.cfd_b200_step(None, None, 1.0, 1.0, None, 0.0, None) == -1
+    assert L.cfd_b200_upload(None, None, None, None) == -1
+    assert L.cfd_b200_launch_count(None) == 0

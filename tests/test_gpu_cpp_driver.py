@@ -111,3 +111,57 @@ def test_eager_coherence_is_a_true_drop_in(exe, port, tmp_path):
     assert r.returncode == 0, r.stderr
     raw = np.fromfile(dump)
     assert np.array_equal(raw[:u.size].view(np.uint64), u.ravel().view(np.uint64))
+
+
+def test_eager_drop_in_like_the_gui_loop(exe, port, tmp_path):
+    """cpp/test_dropin.cpp: TimeIntegrator::step in eager mode with dt_override and a host-side edit of State between
+    steps (the GUI's shapes), then every public free function on caller arrays -- all against the oracle, bit for bit
+    (mg path / stencil stages) or within the PCG tolerance."""
+    import ctypes as C
+    prog = os.path.join(ROOT, "macos-cfd_b200", "lib", "test_dropin")
+    r = subprocess.run([prog, str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    nx, ny, Lx, Ly = 72, 40, 1.8, 1.0
+    bc, Re, CFL = cfdo.preset("lid", Ly)
+    sim = cfdo.Sim(port, nx, ny, Lx, Ly)
+    want = []
+    for _ in range(6):
+        dt = sim.step(bc, 1000.0, 0.1, cfdo.make_params("mg", vcycles=2), dt_override=0.0005)
+        want.append((dt, sim.last_residual, port.divergence_l2(nx, ny, Lx, Ly, sim.u, sim.v),
+                     port.max_velocity(nx, ny, Lx, Ly, sim.u, sim.v)))
+        sim.u[10:14, 20:26] *= 0.1
+    lines = (tmp_path / "log.txt").read_text().splitlines()
+    for line, w in zip(lines, want):
+        got = [float(x) for x in line.split()]
+        assert got[0] == w[0] and got[3] == w[3]
+        assert abs(got[1] - w[1]) <= 1e-12 * w[1] and abs(got[2] - w[2]) <= 1e-12 * w[2]
+    sh = cfdo.shapes(nx, ny)
+
+    def load(name, key):
+        return np.fromfile(tmp_path / name).reshape(sh[key])
+
+    def same(a, b):
+        return np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+    assert same(load("u.bin", "u"), sim.u) and same(load("v.bin", "v"), sim.v) and same(load("p.bin", "p"), sim.p)
+    assert same(load("rhs.bin", "p")[1:-1, 1:-1], sim.rhs[1:-1, 1:-1])
+    # free functions
+    u2, v2, p2 = sim.u.copy(), sim.v.copy(), sim.p.copy()
+    jet = cfdo.make_bc(cfdo.INFLOW, cfdo.OUTFLOW, cfdo.WALL, cfdo.WALL, left_inflow_u=1.0, jet_center=0.5, jet_width=0.18)
+    port.apply_bc("u", nx, ny, Lx, Ly, u2, jet)
+    port.apply_bc("v", nx, ny, Lx, Ly, v2, jet)
+    port.apply_bc("p", nx, ny, Lx, Ly, p2, jet)
+    assert float(lines[6]) == port.compute_cfl(nx, ny, Lx, Ly, u2, v2, 50.0, 0.01)
+    du = np.zeros(sh["u"])
+    port.advect_u(nx, ny, Lx, Ly, u2, v2, du)
+    port.diffuse_u(nx, ny, Lx, Ly, u2, du, 1.0 / 50.0)
+    rhs2 = np.zeros(sh["p"])
+    port.divergence(nx, ny, Lx, Ly, u2, v2, rhs2)
+    port.subtract_grad_p(nx, ny, Lx, Ly, u2, v2, p2, 1e-3)
+    res, iters = port.pressure_solve(nx, ny, Lx, Ly, p2, rhs2, cfdo.make_params("pcg", tol=1e-9, pcg_max_iters=30))
+    assert same(load("f_du.bin", "u"), du) and same(load("f_rhs.bin", "p")[1:-1, 1:-1], rhs2[1:-1, 1:-1])
+    assert same(load("f_u.bin", "u"), u2) and same(load("f_v.bin", "v"), v2)
+    gp = load("f_p.bin", "p")
+    assert np.linalg.norm(gp - p2) <= 1e-10 * np.linalg.norm(p2)
+    gres, giters = lines[7].split()
+    assert abs(float(gres) - res) <= 1e-8 * res and abs(int(giters) - iters) <= 1

@@ -400,3 +400,24 @@ def test_full_size_properties_8192(cfd):
     u3 = np.empty_like(u)
     t.download(u=u3)
     assert same(u, u3)
+
+
+def test_largest_single_gpu_grid_16384(cfd):
+    """16384 x 16384 fp64 (2.1 GB per field, element offsets beyond 2^31 bytes): one mg step and 3 PCG iterations run,
+    stay finite, are reproducible, and the lid row carries the imposed value."""
+    nx = ny = 16384
+    bc, Re, CFL = cfd.preset("lid", 1.0)
+    s = cfd.Solver(nx, ny, 1.0, 1.0)
+    a = s.step(bc, Re, CFL, cfd.make_params("mg", vcycles=2))
+    b = s.step(bc, Re, CFL, cfd.make_params("pcg", pcg_max_iters=3))
+    assert a.nonfinite == 0 and b.nonfinite == 0 and b.iters == 3 and np.isfinite(b.residual)
+    assert a.dt == 1e-6  # pinned to the floor of compute_cfl at this resolution (SURVEY appendix A)
+    u = np.empty((ny + 2, nx + 3))
+    s.download(u=u)
+    assert np.isfinite(u).all() and (u[ny, 1:nx + 2] == 1.0).all() and abs(u[1:ny, 2:nx + 1]).max() > 0
+    d1 = s.divergence_l2()
+    s.close()
+    t = cfd.Solver(nx, ny, 1.0, 1.0)
+    t.step(bc, Re, CFL, cfd.make_params("mg", vcycles=2))
+    t.step(bc, Re, CFL, cfd.make_params("pcg", pcg_max_iters=3))
+    assert t.divergence_l2() == d1
