@@ -18,6 +18,7 @@
 #include "kernels_rbgs_fused.cuh"
 #include "kernels_vcycle.cuh"
 #include "kernels_pcg_march.cuh"
+#include "kernels_pcg_coop.cuh"
 
 namespace {
 
@@ -76,6 +77,9 @@ struct cfd_b200_solver {
     int mg_nlev = 0;
     MgLevel mg[MG_CTA_MAXLEV + 4] = {};
     int mg_cta_smem_max = 0;
+    // cooperative persistent PCG (small grids)
+    double *coop_xrows = nullptr, *coop_slots = nullptr;
+    int coop_ok = -1, coop_rows = 0, coop_blocks = 0, coop_smem = 0; // -1 = not probed yet
 };
 
 namespace {
@@ -382,6 +386,29 @@ int enqueue_vcycle(cfd_b200_solver *s, const cfd_b200_params *pp, double Lx, dou
     return 0;
 }
 
+// Can this handle run the cooperative persistent PCG kernel (working set in shared memory, all blocks co-resident)?
+bool coop_probe(cfd_b200_solver *s) {
+    if (s->coop_ok >= 0) return s->coop_ok != 0;
+    s->coop_ok = 0;
+    static const int env = getenv("CFD_B200_PCG_COOP") ? atoi(getenv("CFD_B200_PCG_COOP")) : 1;
+    const Geom &g = s->g;
+    int coop = 0;
+    if (!env || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s->device) != cudaSuccess || !coop) return false;
+    const int nblk = s->sm_count, R = cdiv(g.ny, nblk);
+    const size_t smem = (size_t)(3 * R + 2) * (g.nx + 2) * sizeof(double);
+    if (smem > 200 * 1024) return false;
+    if (cudaFuncSetAttribute(k_pcg_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_coop, PC_THREADS, smem) != cudaSuccess || per_sm < 1) return false;
+    if (cudaMalloc(&s->coop_xrows, (size_t)2 * nblk * 2 * (g.nx + 2) * sizeof(double)) != cudaSuccess) return false;
+    if (cudaMalloc(&s->coop_slots, (size_t)3 * 2 * nblk * sizeof(double)) != cudaSuccess) return false;
+    cudaMemsetAsync(s->coop_xrows, 0, (size_t)2 * nblk * 2 * (g.nx + 2) * sizeof(double), s->stream);
+    cudaMemsetAsync(s->coop_slots, 0, (size_t)3 * 2 * nblk * sizeof(double), s->stream);
+    s->coop_rows = R, s->coop_blocks = nblk, s->coop_smem = (int)smem;
+    s->coop_ok = 1;
+    return true;
+}
+
 // PressureSolver::solve, pressure.cpp:113-242.  The whole solve is enqueued; convergence is tested on the device.
 // Row slabs: every grid-level sum is completed by an allreduce + a one-thread tail kernel (identical on all ranks),
 // and the rows a neighbour's stencil reads are exchanged where the single-GPU path would simply read them.
@@ -390,6 +417,15 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
     const int single = s->nranks == 1;
     if (pp->solver == CFD_B200_SOLVER_PCG) {
         cudaMemsetAsync(s->p, 0, s->n * sizeof(double), s->stream); // pressure.cpp:133-134
+        if (single && s->variant != 0 && coop_probe(s)) { // small grid: the whole solve in one persistent kernel
+            PcgCoopArgs a{g, s->rhs, s->p, s->coop_xrows, s->coop_slots, s->d_sc, pp->tol, pp->pcg_max_iters, s->coop_rows};
+            void *args[] = {&a};
+            CU(cudaLaunchCooperativeKernel((void *)k_pcg_coop, dim3(s->coop_blocks), dim3(PC_THREADS), args,
+                                           (size_t)s->coop_smem, s->stream));
+            s->launches++;
+            LAUNCH(s, k_solve_finish, 1, 1, s->d_sc);
+            return 0;
+        }
         {
             dim3 grid(cdiv(g.nx, 512), g.ny < 256 ? g.ny : 256);
             LAUNCH(s, k_pcg_init, grid, PT_THREADS, g, s->rhs, s->r, s->d_sc, s->partials, pp->tol, pp->pcg_max_iters, single);
@@ -719,6 +755,8 @@ void cfd_b200_destroy(cfd_b200_solver *s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->comm) nccl_api().CommDestroy(s->comm);
     if (s->gathered) cudaFree(s->gathered);
+    if (s->coop_xrows) cudaFree(s->coop_xrows);
+    if (s->coop_slots) cudaFree(s->coop_slots);
     for (int l = 1; l < s->mg_nlev; ++l) {
         if (s->mg[l].p) cudaFree(s->mg[l].p);
         if (s->mg[l].rhs) cudaFree(s->mg[l].rhs);
