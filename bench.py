@@ -169,7 +169,10 @@ def main():
               "grid": f"{nx}x{ny}", "domain": f"{Lx}x{Ly}", "vcycles": vcycles, "tol": tol, "pcg_max_iters": iters,
               "decomposition": f"{N} row slab(s) of {nx}x{ny_gpu}",
               "l2": "fields (>= 0.5 GB each) exceed the 126 MB L2" if nx * ny_gpu * 8 > 200e6 else
-              "L2 flushed (256 MB write) before every timed step"}
+              "L2 flushed (256 MB write) before every timed step",
+              "timing": "CUDA events on the solver's stream, max over ranks" +
+                        ("; mg diverges by design, so the K steps are timed in chunks of <= 8 from the reset state"
+                         if solver == "mg" else "")}
     base = {"metric": "cell-updates/s (full timestep incl. Poisson)", "unit": "cell-updates/s", "n_gpus": N,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic (deterministic preset initial/boundary data)",
@@ -244,18 +247,31 @@ def main():
     sampler.start()
     l0 = s.launch_count
     barrier()
+    # The reference's `mg` mode diverges to inf within ~20-30 steps; once values overflow, the
+    # non-finite slow paths run and the timing no longer describes the solver.  mg workloads are therefore timed in
+    # chunks of <= 8 steps, each starting from the reset state; the (device-side) resets sit outside the timed events.
+    chunk = 8 if (solver == "mg" and preset != "shear") else args.steps
     if flush is None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(args.steps):
-            s.step_async(bc, Re, CFL, pp)
-        e1.record(stream)
-        info = s.sync()
-        barrier()
-        total_ms = max_over_ranks(e0.elapsed_time(e1))
+        total_ms, left = 0.0, args.steps
+        while left > 0:
+            n = min(chunk, left)
+            if chunk < args.steps:
+                s.reset()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(n):
+                s.step_async(bc, Re, CFL, pp)
+            e1.record(stream)
+            info = s.sync()
+            barrier()
+            total_ms += max_over_ranks(e0.elapsed_time(e1))
+            left -= n
     else:
         total_ms = 0.0
-        for _ in range(args.steps):
+        for i in range(args.steps):
+            if chunk < args.steps and i > 0 and i % chunk == 0:
+                s.reset()
             with torch.cuda.stream(stream):
                 flush.fill_(1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -127,6 +127,8 @@ int cfd_b200_download_work(cfd_b200_solver *s, double *u1, double *v1);
 
 /* TimeIntegrator::clear_work (time_integrator.cpp:38-45) */
 int cfd_b200_clear_work(cfd_b200_solver *s);
+/* The drivers' reset (main.cpp:113-126, :338-346): u, v, p, rhs and the work arrays zeroed on the device, asynchronously. */
+int cfd_b200_reset(cfd_b200_solver *s);
 
 /* TimeIntegrator::step (time_integrator.hpp:27-29, time_integrator.cpp:47-239) on the device-resident State.
  * Synchronous: returns when the step is complete; *info (may be NULL) receives dt, residual, ... */

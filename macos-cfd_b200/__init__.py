@@ -130,6 +130,7 @@ def load_library(build: bool = True):
     L.cfd_b200_download.argtypes = [S, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cfd_b200_download_work.argtypes = [S, C.c_void_p, C.c_void_p]
     L.cfd_b200_clear_work.argtypes = [S]
+    L.cfd_b200_reset.argtypes = [S]
     L.cfd_b200_step.argtypes = [S, C.POINTER(BC), C.c_double, C.c_double, C.POINTER(Params), C.c_double,
                                 C.POINTER(StepInfo)]
     L.cfd_b200_step_async.argtypes = [S, C.POINTER(BC), C.c_double, C.c_double, C.POINTER(Params), C.c_double]
@@ -232,6 +233,10 @@ class Solver:
 
     def clear_work(self):
         self._check(self.L.cfd_b200_clear_work(self.h))
+
+    def reset(self):
+        """Device-side zero of the State and work arrays (the GUI's reset, main.cpp:338-346); asynchronous."""
+        self._check(self.L.cfd_b200_reset(self.h))
 
     def step(self, bc, Re, CFL, pp, dt_override=0.0) -> StepInfo:
         info = StepInfo()

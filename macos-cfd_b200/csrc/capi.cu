@@ -818,6 +818,16 @@ int cfd_b200_download_work(cfd_b200_solver *s, double *u1, double *v1) {
     return 0;
 }
 
+// The GUI's reset (main.cpp:338-346): every State field and work array back to zero, on the device.
+int cfd_b200_reset(cfd_b200_solver *s) {
+    if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
+    CU(cudaSetDevice(s->device));
+    double *fields[] = {s->u, s->v, s->p, s->p_alt, s->rhs, s->u1, s->v1};
+    for (double *f : fields) CU(cudaMemsetAsync(f, 0, s->n * sizeof(double), s->stream));
+    s->cfl_cached = false, s->halo_uv_valid = false;
+    return 0;
+}
+
 int cfd_b200_clear_work(cfd_b200_solver *s) {
     if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
     CU(cudaSetDevice(s->device));
