@@ -206,6 +206,9 @@ def main():
     pp = cfd.make_params(solver, vcycles=vcycles, tol=tol, pcg_max_iters=iters)
     s = cfd.Solver(nx, ny, Lx, Ly, device=local_rank, rank=rank, nranks=N, comm_id=comm)
     s.set_variant(args.variant)
+    config["comm"] = {"single": "none (one GPU)", "nccl": "NCCL send/recv rows + allreduce",
+                      "p2p": "peer memory over NVLink (CUDA IPC): halo rows stored into the neighbour's arrays, "
+                             "reductions fused with their scalar tails"}[s.comm_mode]
     sh = s.shapes()
 
     def barrier():

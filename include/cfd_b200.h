@@ -111,6 +111,10 @@ int cfd_b200_create(int nx, int ny, double Lx, double Ly, int device, cfd_b200_s
 int cfd_b200_comm_id(void *id128);
 int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int rank, int nranks,
                          const void *nccl_id128, cfd_b200_solver **out);
+/* How this handle talks to the other slabs: 0 = single GPU, 1 = NCCL send/recv + allreduce, 2 = peer memory over
+ * NVLink (CUDA IPC: halo rows stored straight into the neighbour's arrays, reductions fused with their scalar tails).
+ * 2 is chosen when every rank could map every peer; CFD_B200_P2P=0 in the environment forces 1. */
+int cfd_b200_comm_mode(const cfd_b200_solver *s);
 /* First owned cell row and number of owned cell rows of this handle (0, ny for a single-GPU handle). */
 int cfd_b200_slab_rows(const cfd_b200_solver *s, int *row0, int *nrows);
 

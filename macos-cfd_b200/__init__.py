@@ -123,6 +123,7 @@ def load_library(build: bool = True):
                                        C.POINTER(S)]
     L.cfd_b200_comm_id.argtypes = [C.c_void_p]
     L.cfd_b200_slab_rows.argtypes = [S, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.cfd_b200_comm_mode.argtypes = [S]
     L.cfd_b200_destroy.argtypes = [S]
     L.cfd_b200_destroy.restype = None
     L.cfd_b200_upload.argtypes = [S, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -200,6 +201,11 @@ class Solver:
         r0, nr = C.c_int(), C.c_int()
         self._check(self.L.cfd_b200_slab_rows(self.h, C.byref(r0), C.byref(nr)))
         self.row0, self.nrows = r0.value, nr.value  # owned cell rows [row0, row0 + nrows)
+
+    @property
+    def comm_mode(self) -> str:
+        """How the slabs talk: "single", "nccl" (send/recv + allreduce) or "p2p" (peer memory over NVLink, CUDA IPC)."""
+        return ("single", "nccl", "p2p")[self.L.cfd_b200_comm_mode(self.h)]
 
     def _check(self, rc):
         if rc != 0:

@@ -3,12 +3,14 @@
 // enqueue_step().  No CPU fallback exists: every entry point needs a CUDA device.
 #include "../../include/cfd_b200.h"
 
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 
 #include "comm.cuh"
 #include "common.cuh"
@@ -19,6 +21,7 @@
 #include "kernels_vcycle.cuh"
 #include "kernels_pcg_march.cuh"
 #include "kernels_pcg_coop.cuh"
+#include "p2p.cuh"
 
 namespace {
 
@@ -52,6 +55,7 @@ struct cfd_b200_solver {
     int rank = 0, nranks = 1;
     double Lx = 1.0, Ly = 1.0;
     size_t n = 0; // doubles per field
+    double *arena = nullptr; // the NFIELDS fields below + this rank's P2PBlock in ONE allocation (one IPC handle per rank)
     double *u = nullptr, *v = nullptr, *p = nullptr, *rhs = nullptr;
     double *p_alt = nullptr; // ping-pong partner of p for the fused red-black smoother
     double *u1 = nullptr, *v1 = nullptr;           // TimeIntegrator work arrays (time_integrator.hpp:18-19)
@@ -64,6 +68,7 @@ struct cfd_b200_solver {
     cudaStream_t stream = nullptr;
     long long launches = 0;
     int variant = 1;
+    int pdl = 1; // programmatic dependent launch between consecutive kernels (CFD_B200_PDL=0 turns it off)
     bool cfl_cached = false;   // umax/vmax of the current device State are already in d_sc (from the last step)
     cfd_b200_bc last_bc{};
     int profiling = 0;
@@ -71,6 +76,13 @@ struct cfd_b200_solver {
     bool ev_valid = false;
     int sm_count = 148;
     ncclComm_t comm = nullptr; // row slabs only
+    // peer-memory path (p2p.cuh): every rank's arena mapped through CUDA IPC
+    bool p2p_on = false;
+    void *peer_arena[P2P_MAXR] = {};
+    size_t peer_n[P2P_MAXR] = {};
+    int peer_ny[P2P_MAXR] = {};
+    P2PBlock *blk[P2P_MAXR] = {};
+    unsigned long long halo_epoch = 0, red_epoch = 0;
     double *gathered = nullptr; // 4 doubles per rank (k_slab_pack / k_slab_unpack)
     bool halo_uv_valid = false; // the 2 halo rows of u, v are current (set by the exchange that ends a step)
     // V-cycle extension: coarse levels (level 0 aliases p / rhs), allocated on first use
@@ -84,11 +96,19 @@ struct cfd_b200_solver {
 
 namespace {
 
-#define LAUNCH(s, kernel, grid, block, ...)                                                                     \
-    do {                                                                                                        \
-        kernel<<<grid, block, 0, (s)->stream>>>(__VA_ARGS__);                                                   \
-        (s)->launches++;                                                                                        \
-    } while (0)
+// Every kernel launch of the path: programmatic stream serialization (see pdl_begin(), common.cuh) unless disabled.
+template <class... KArgs, class... Args>
+inline void launch_k(cfd_b200_solver *s, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = s->pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    s->launches++;
+}
+#define LAUNCH(s, kernel, grid, block, ...) launch_k(s, kernel, dim3(grid), dim3(block), 0, __VA_ARGS__)
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
@@ -153,6 +173,8 @@ void enqueue_bc(cfd_b200_solver *s, const BcD &bc, double *u, double *v, double 
     if (g.bottom || g.top) LAUNCH(s, k_bc_bt, cdiv(g.nx + 3, 128), 128, g, bc, u, v, p, sanitize, s->d_sc);
 }
 
+int reduce_fin(cfd_b200_solver *s, int kind, double tol, int max_iters);
+
 void enqueue_cfl(cfd_b200_solver *s, double Re, double CFL, double dt_override, int cfl_only) {
     const Geom &g = s->g;
     if (!s->cfl_cached) {
@@ -162,8 +184,7 @@ void enqueue_cfl(cfd_b200_solver *s, double Re, double CFL, double dt_override, 
         cudaMemsetAsync(&s->d_sc->umax_bits, 0, 2 * sizeof(unsigned long long), s->stream);
         dim3 grid(cdiv(g.P / 2, 256), g.ny + 1 < 64 ? g.ny + 1 : 64);
         LAUNCH(s, k_absmax, grid, 256, g, s->u, s->v, s->d_sc);
-        // non-negative doubles order like their bit patterns, so the maxima can be all-reduced as doubles
-        if (s->nranks > 1) nccl_api().AllReduce(&s->d_sc->umax_bits, &s->d_sc->umax_bits, 2, ncclDouble, ncclMax, s->comm, s->stream);
+        reduce_fin(s, RED_CFL, 0.0, 0);
     }
     s->cfl_cached = false;
     LAUNCH(s, k_dt, 1, 1, g, Re, CFL, dt_override, s->d_sc, cfl_only);
@@ -198,8 +219,13 @@ void enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, const doub
         return;
     }
     static const int ry_env = getenv("CFD_B200_RHS_RY") ? atoi(getenv("CFD_B200_RHS_RY")) : 0;
-    const int RY = ry_env > 0 ? ry_env : 64;
-    dim3 mgrid(cdiv(cdiv(XB - XA + 1, MARCH_COLS), MARCH_WARPS), cdiv(YB - YA + 1, RY));
+    // Rows per strip: 64 on grids that fill the GPU; smaller grids get shorter strips until the launch has one full
+    // wave of blocks (148 SMs x MARCH_MINBLOCKS) -- at 1024^2, 64-row strips are only 80 blocks (2 warps per SM).
+    int RY = 64;
+    const int gxm = cdiv(cdiv(XB - XA + 1, MARCH_COLS), MARCH_WARPS);
+    while (RY > 8 && (long long)gxm * cdiv(YB - YA + 1, RY) < (long long)s->sm_count * MARCH_MINBLOCKS) RY /= 2;
+    if (ry_env > 0) RY = ry_env;
+    dim3 mgrid(gxm, cdiv(YB - YA + 1, RY));
     LAUNCH(s, k_rhs_march<MODE>, mgrid, 32 * MARCH_WARPS, g, k, uin, vin, uout, vout, s->d_sc, XA, XB, YA, YB, RY);
     add(0, 0, ntx, tyb);                    // bottom strip
     add(0, tyt, ntx, nty - tyt);            // top strip
@@ -244,10 +270,132 @@ enum { HALO_UP = 1, HALO_DOWN = 2, HALO_BOTH = 3 }; // direction in which OWNED 
                                            nccl_api().GetErrorString(r_));                                      \
     } while (0)
 
+#define TRY(call)                                                                                               \
+    do {                                                                                                        \
+        int rc_ = (call);                                                                                       \
+        if (rc_) return rc_;                                                                                    \
+    } while (0)
+
+#define NFIELDS 10 // u, v, p, p_alt, rhs, u1, v1, r, sA, sB: arena slots of n doubles each
+
+// ---- peer-memory bootstrap: exchange CUDA IPC handles over NCCL, map every peer's arena, verify, agree ------------
+struct P2PInfo {
+    cudaIpcMemHandle_t handle;
+    unsigned long long n; // doubles per field on that rank (slabs may differ by one row)
+    int ny;
+    int ok;
+};
+
+// Wait for the stream, but never for more than `seconds` (a dead peer must not hang teardown).
+bool bounded_sync(cfd_b200_solver *s, double seconds) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        cudaError_t e = cudaStreamQuery(s->stream);
+        if (e == cudaSuccess) return true;
+        if (e != cudaErrorNotReady) { cudaGetLastError(); return false; }
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > seconds) return false;
+        std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
+}
+
+void p2p_unmap(cfd_b200_solver *s) {
+    for (int r = 0; r < s->nranks; ++r) {
+        if (r != s->rank && s->peer_arena[r]) {
+            cudaIpcCloseMemHandle(s->peer_arena[r]);
+            s->peer_arena[r] = nullptr;
+            s->blk[r] = nullptr;
+        }
+    }
+    cudaGetLastError();
+}
+
+int p2p_setup(cfd_b200_solver *s) {
+    static const int env = getenv("CFD_B200_P2P") ? atoi(getenv("CFD_B200_P2P")) : 1;
+    NcclApi &nc = nccl_api();
+    const int R = s->nranks;
+    P2PInfo mine{};
+    mine.n = s->n, mine.ny = s->g.ny;
+    const unsigned long long magic = P2P_MAGIC + (unsigned long long)s->rank;
+    mine.ok = env && cudaMemcpyAsync(&s->blk[s->rank]->magic, &magic, sizeof(magic), cudaMemcpyHostToDevice, s->stream) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.handle, s->arena) == cudaSuccess;
+    cudaGetLastError();
+    // all-gather of the descriptors (bytes) on the solver's stream: ordered after the arena memset and the magic
+    P2PInfo *d_all = nullptr;
+    CU(cudaMalloc(&d_all, (size_t)R * sizeof(P2PInfo)));
+    CU(cudaMemcpyAsync(d_all + s->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, s->stream));
+    NCCLCHK(nc.AllGather(d_all + s->rank, d_all, sizeof(P2PInfo), ncclInt8, s->comm, s->stream));
+    P2PInfo all[P2P_MAXR];
+    CU(cudaMemcpyAsync(all, d_all, (size_t)R * sizeof(P2PInfo), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    int ok = 1;
+    for (int r = 0; r < R; ++r) ok &= all[r].ok;
+    for (int r = 0; r < R && ok; ++r) {
+        s->peer_n[r] = (size_t)all[r].n, s->peer_ny[r] = all[r].ny;
+        if (r == s->rank) continue;
+        void *ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+        s->peer_arena[r] = ptr;
+        s->blk[r] = reinterpret_cast<P2PBlock *>(static_cast<double *>(ptr) + (size_t)NFIELDS * s->peer_n[r]);
+        unsigned long long seen = 0; // read the peer's magic THROUGH the mapping: proves base address and peer access
+        if (cudaMemcpy(&seen, &s->blk[r]->magic, sizeof(seen), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            seen != P2P_MAGIC + (unsigned long long)r)
+            ok = 0;
+    }
+    cudaGetLastError();
+    // every rank must take the same path: min over ranks of `ok`
+    double okd = ok;
+    CU(cudaMemcpyAsync(s->gathered, &okd, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    NCCLCHK(nc.AllReduce(s->gathered, s->gathered, 1, ncclDouble, ncclMin, s->comm, s->stream));
+    CU(cudaMemcpyAsync(&okd, s->gathered, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    cudaFree(d_all);
+    s->p2p_on = okd > 0.5;
+    if (!s->p2p_on) p2p_unmap(s);
+    s->peer_arena[s->rank] = s->arena;
+    return 0;
+}
+
+// Peers store into my arena and I into theirs: nobody may unmap or free before everybody has stopped (two barriers).
+void p2p_teardown(cfd_b200_solver *s) {
+    if (!s->p2p_on || !s->comm) return;
+    NcclApi &nc = nccl_api();
+    bool alive = nc.AllReduce(s->gathered, s->gathered, 1, ncclDouble, ncclMin, s->comm, s->stream) == ncclSuccess && bounded_sync(s, 10.0);
+    p2p_unmap(s);
+    if (alive) alive = nc.AllReduce(s->gathered, s->gathered, 1, ncclDouble, ncclMin, s->comm, s->stream) == ncclSuccess && bounded_sync(s, 10.0);
+    s->p2p_on = false;
+}
+
+// Peer-memory version of the exchange below: one kernel, plain stores into the neighbours' halo rows (p2p.cuh).
+int halo_exchange_p2p(cfd_b200_solver *s, double *const *fields, int nfields, int rows, int dirs) {
+    const Geom &g = s->g;
+    HaloArgs a{};
+    a.count = (unsigned long long)rows * g.P;
+    a.epoch = ++s->halo_epoch;
+    const int lower = g.bottom ? -1 : s->rank - 1, upper = g.top ? -1 : s->rank + 1;
+    auto rowptr = [&](double *f, int jj) { return f + (size_t)(jj + CFD_YOFF) * g.P; };
+    auto peer_row = [&](int r, size_t fi, int jj) {
+        return static_cast<double *>(s->peer_arena[r]) + fi * s->peer_n[r] + (size_t)(jj + CFD_YOFF) * g.P;
+    };
+    for (int k = 0; k < nfields; ++k) {
+        double *f = fields[k];
+        const size_t fi = (size_t)(f - s->arena) / s->n;
+        if (f < s->arena || fi >= NFIELDS) return fail(CFD_B200_EINVAL, "halo exchange of a field outside the arena");
+        if (upper >= 0 && (dirs & HALO_UP)) a.job[a.njobs++] = HaloJob{rowptr(f, g.ny - rows + 1), peer_row(upper, fi, 1 - rows), 1};
+        if (lower >= 0 && (dirs & HALO_DOWN)) a.job[a.njobs++] = HaloJob{rowptr(f, 1), peer_row(lower, fi, s->peer_ny[lower] + 1), 0};
+    }
+    if (lower >= 0) a.peer_enter[0] = &s->blk[lower]->enter_flag[1], a.peer_data[0] = &s->blk[lower]->data_flag[1];
+    if (upper >= 0) a.peer_enter[1] = &s->blk[upper]->enter_flag[0], a.peer_data[1] = &s->blk[upper]->data_flag[0];
+    int grid = (int)((a.count / 2 + 255) / 256);
+    grid = grid < 1 ? 1 : (grid > 32 ? 32 : grid);
+    LAUNCH(s, k_halo_xchg, grid, 256, a, s->blk[s->rank], s->d_sc);
+    return 0;
+}
+
 // Send the top `rows` owned rows of each field to the slab above (HALO_UP) and/or the bottom `rows` owned rows to the
 // slab below (HALO_DOWN); receive the neighbours' rows into the halo rows.  Rows are contiguous: one message each.
 int halo_exchange(cfd_b200_solver *s, double *const *fields, int nfields, int rows, int dirs) {
     if (s->nranks == 1) return 0;
+    if (s->p2p_on) return halo_exchange_p2p(s, fields, nfields, rows, dirs);
     const Geom &g = s->g;
     NcclApi &n = nccl_api();
     const size_t cnt = (size_t)rows * g.P;
@@ -271,26 +419,65 @@ int halo_exchange2(cfd_b200_solver *s, double *a, double *b, int rows, int dirs)
     double *f[2] = {a, b};
     return halo_exchange(s, f, b ? 2 : 1, rows, dirs);
 }
-// in-place allreduce of `count` doubles in device memory (PCG dots, residual, CFL maxima, divergence sums)
+// in-place allreduce of `count` doubles in device memory (NCCL path)
 int allreduce(cfd_b200_solver *s, void *dev, int count, ncclRedOp_t op) {
     if (s->nranks == 1) return 0;
     NCCLCHK(nccl_api().AllReduce(dev, dev, (size_t)count, ncclDouble, op, s->comm, s->stream));
     return 0;
 }
-#define TRY(call)                                                                                               \
-    do {                                                                                                        \
-        int rc_ = (call);                                                                                       \
-        if (rc_) return rc_;                                                                                    \
-    } while (0)
+// Row slabs: complete a grid-level reduction across ranks and run the scalar tail that consumes it (RED_* of p2p.cuh).
+// Peer-memory path: one fused kernel.  NCCL path: allreduce / all-gather + a one-thread tail kernel.
+int reduce_fin(cfd_b200_solver *s, int kind, double tol, int max_iters) {
+    if (s->nranks == 1) return 0;
+    if (s->p2p_on) {
+        RedArgs a{};
+        for (int r = 0; r < s->nranks; ++r) a.blk[r] = s->blk[r];
+        a.nranks = s->nranks, a.rank = s->rank, a.kind = kind, a.epoch = ++s->red_epoch, a.tol = tol, a.max_iters = max_iters;
+        LAUNCH(s, k_p2p_reduce, 1, 32, a, s->d_sc);
+        return 0;
+    }
+    switch (kind) {
+    case RED_PCG_INIT:
+        TRY(allreduce(s, s->d_sc->red, 2, ncclSum));
+        LAUNCH(s, k_pcg_fin_init, 1, 1, s->d_sc, tol, max_iters);
+        break;
+    case RED_PCG1:
+        TRY(allreduce(s, s->d_sc->red, 1, ncclSum));
+        LAUNCH(s, k_pcg_fin1, 1, 1, s->d_sc);
+        break;
+    case RED_PCG2:
+        TRY(allreduce(s, s->d_sc->red, 2, ncclSum));
+        LAUNCH(s, k_pcg_fin2, 1, 1, s->d_sc, tol, max_iters);
+        break;
+    case RED_RBGS:
+        TRY(allreduce(s, s->d_sc->red, 1, ncclSum));
+        LAUNCH(s, k_rbgs_fin, 1, 1, s->d_sc, tol);
+        break;
+    case RED_STEP_END: // one collective: CFL maxima of the next step + the two partial sums of squares
+        LAUNCH(s, k_slab_pack, 1, 1, s->d_sc);
+        NCCLCHK(nccl_api().AllGather(s->d_sc->red, s->gathered, 4, ncclDouble, s->comm, s->stream));
+        LAUNCH(s, k_slab_unpack, 1, 1, s->d_sc, s->gathered, s->nranks);
+        break;
+    case RED_CFL: // non-negative doubles order like their bit patterns, so the maxima can be all-reduced as doubles
+        TRY(allreduce(s, &s->d_sc->umax_bits, 2, ncclMax));
+        break;
+    case RED_DIAG:
+        TRY(allreduce(s, &s->d_sc->diag_sum, 1, ncclSum));
+        TRY(allreduce(s, &s->d_sc->diag_max_bits, 1, ncclMax));
+        break;
+    default:
+        return fail(CFD_B200_EINVAL, "bad reduction kind %d", kind);
+    }
+    return 0;
+}
 
 template <int POW2>
 void launch_fused(cfd_b200_solver *s, double tol, int ntx, int nty, int finish) {
     const Geom &g = s->g;
     if ((1 + g.j0) & 1)
-        k_rbgs_fused<POW2, 1><<<ntx * nty, RB_THREADS, RB_SMEM, s->stream>>>(g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, ntx, finish);
+        launch_k(s, k_rbgs_fused<POW2, 1>, dim3(ntx * nty), dim3(RB_THREADS), RB_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, ntx, finish);
     else
-        k_rbgs_fused<POW2, 0><<<ntx * nty, RB_THREADS, RB_SMEM, s->stream>>>(g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, ntx, finish);
-    s->launches++;
+        launch_k(s, k_rbgs_fused<POW2, 0>, dim3(ntx * nty), dim3(RB_THREADS), RB_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, ntx, finish);
 }
 
 // ---- EXTENSION: true geometric V-cycle (kernels_vcycle.cuh; algorithm = the CPU restatement cfd_vcycle.c of the test tree; parity unpinned) ----
@@ -299,7 +486,7 @@ int vcycle_levels(int nx, int ny, int mg_levels) {
     while (n < mg_levels && n < MG_CTA_MAXLEV + 3 && nx % 2 == 0 && ny % 2 == 0 && nx / 2 >= 4 && ny / 2 >= 4) nx /= 2, ny /= 2, ++n;
     return n;
 }
-int enqueue_vcycle(cfd_b200_solver *s, const cfd_b200_params *pp, double Lx, double Ly) {
+int enqueue_vcycle(cfd_b200_solver *s, const cfd_b200_params *pp, double Lx, double Ly, bool in_step) {
     const Geom &g = s->g;
     if (s->nranks > 1) return fail(CFD_B200_EUNSUPPORTED, "mg_mode=VCYCLE is single-GPU in this version");
     const int nlev = vcycle_levels(g.nx, g.ny, pp->mg_levels);
@@ -359,7 +546,7 @@ int enqueue_vcycle(cfd_b200_solver *s, const cfd_b200_params *pp, double Lx, dou
         for (int k = 0; k < n; ++k)
             for (int colour = 0; colour < 2; ++colour) LAUNCH(s, k_mg_colour, grid, block, L, colour, s->d_sc);
     };
-    LAUNCH(s, k_solve_begin, 1, 1, s->d_sc);
+    if (!in_step) LAUNCH(s, k_solve_begin, 1, 1, s->d_sc);
     LAUNCH(s, k_mg_zero_ghosts, cdiv((g.nx > g.ny ? g.nx : g.ny) + 2, 128), 128, s->mg[0], s->d_sc);
     const int top = lc < nlev ? lc : nlev - 1; // levels [0, top) run as global-memory kernels on the way down
     for (int vc = 0; vc < pp->vcycles; ++vc) {
@@ -369,8 +556,7 @@ int enqueue_vcycle(cfd_b200_solver *s, const cfd_b200_params *pp, double Lx, dou
             LAUNCH(s, k_mg_restrict, dim3(cdiv(C.nx, 32), cdiv(C.ny, 8)), dim3(32, 8), s->mg[l], C, s->d_sc);
         }
         if (lc < nlev) {
-            k_mg_coarse_cta<<<1, 1024, cta_smem, s->stream>>>(s->mg[lc], plan, s->d_sc);
-            s->launches++;
+            launch_k(s, k_mg_coarse_cta, dim3(1), dim3(1024), (size_t)cta_smem, s->mg[lc], plan, s->d_sc);
         } else {
             smooth(s->mg[nlev - 1], nlev == 1 ? sweeps : 16 * sweeps);
         }
@@ -382,7 +568,7 @@ int enqueue_vcycle(cfd_b200_solver *s, const cfd_b200_params *pp, double Lx, dou
         dim3 rgrid(cdiv(g.nx, 256), g.ny < 256 ? g.ny : 256);
         LAUNCH(s, k_mg_residual_norm, rgrid, 256, s->mg[0], s->d_sc, s->partials, pp->tol);
     }
-    LAUNCH(s, k_solve_finish, 1, 1, s->d_sc);
+    if (!in_step) LAUNCH(s, k_solve_finish, 1, 1, s->d_sc);
     return 0;
 }
 
@@ -412,7 +598,8 @@ bool coop_probe(cfd_b200_solver *s) {
 // PressureSolver::solve, pressure.cpp:113-242.  The whole solve is enqueued; convergence is tested on the device.
 // Row slabs: every grid-level sum is completed by an allreduce + a one-thread tail kernel (identical on all ranks),
 // and the rows a neighbour's stencil reads are exchanged where the single-GPU path would simply read them.
-int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
+// in_step: k_dt has already done k_solve_begin's resets and k_project will do k_solve_finish's check (two launches less)
+int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp, bool in_step = false) {
     const Geom &g = s->g;
     const int single = s->nranks == 1;
     if (pp->solver == CFD_B200_SOLVER_PCG) {
@@ -423,7 +610,7 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
             CU(cudaLaunchCooperativeKernel((void *)k_pcg_coop, dim3(s->coop_blocks), dim3(PC_THREADS), args,
                                            (size_t)s->coop_smem, s->stream));
             s->launches++;
-            LAUNCH(s, k_solve_finish, 1, 1, s->d_sc);
+            if (!in_step) LAUNCH(s, k_solve_finish, 1, 1, s->d_sc);
             return 0;
         }
         {
@@ -431,8 +618,7 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
             LAUNCH(s, k_pcg_init, grid, PT_THREADS, g, s->rhs, s->r, s->d_sc, s->partials, pp->tol, pp->pcg_max_iters, single);
         }
         if (!single) {
-            TRY(allreduce(s, s->d_sc->red, 2, ncclSum));
-            LAUNCH(s, k_pcg_fin_init, 1, 1, s->d_sc, pp->tol, pp->pcg_max_iters);
+            TRY(reduce_fin(s, RED_PCG_INIT, pp->tol, pp->pcg_max_iters));
             TRY(halo_exchange2(s, s->r, nullptr, 1, HALO_BOTH));
         }
         const int ntx = cdiv(g.nx, PT_X), nty = cdiv(g.ny, PT_Y), ntiles = ntx * nty;
@@ -454,10 +640,7 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
                 LAUNCH(s, k_pcg_phase1_march, mgrid, 32 * PM_WARPS, g, s->r, s_old, s_new, s->d_sc, s->partials, RY, single);
             else
                 LAUNCH(s, k_pcg_phase1, grid, PT_THREADS, g, s->r, s_old, s_new, s->d_sc, s->partials, ntx, ntiles, single);
-            if (!single) {
-                TRY(allreduce(s, s->d_sc->red, 1, ncclSum));
-                LAUNCH(s, k_pcg_fin1, 1, 1, s->d_sc);
-            }
+            if (!single) TRY(reduce_fin(s, RED_PCG1, 0.0, 0));
             if (march)
                 LAUNCH(s, k_pcg_phase2_march, mgrid, 32 * PM_WARPS, g, s->p, s->r, s_new, s->d_sc, s->partials, RY, pp->tol,
                        pp->pcg_max_iters, single);
@@ -465,8 +648,7 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
                 LAUNCH(s, k_pcg_phase2, grid, PT_THREADS, g, s->p, s->r, s_new, s->d_sc, s->partials, ntx, ntiles, pp->tol,
                        pp->pcg_max_iters, single);
             if (!single) {
-                TRY(allreduce(s, s->d_sc->red, 2, ncclSum));
-                LAUNCH(s, k_pcg_fin2, 1, 1, s->d_sc, pp->tol, pp->pcg_max_iters);
+                TRY(reduce_fin(s, RED_PCG2, pp->tol, pp->pcg_max_iters));
                 TRY(halo_exchange2(s, s->r, nullptr, 1, HALO_BOTH)); // the next direction update reads r one row out
             }
             double *t = s_old;
@@ -474,9 +656,9 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
             s_new = t;
         }
     } else {
-        if (pp->mg_mode == CFD_B200_MG_VCYCLE) return enqueue_vcycle(s, pp, s->Lx, s->Ly);
+        if (pp->mg_mode == CFD_B200_MG_VCYCLE) return enqueue_vcycle(s, pp, s->Lx, s->Ly, in_step);
         if (pp->mg_mode != CFD_B200_MG_REFERENCE) return fail(CFD_B200_EINVAL, "bad mg_mode %d", pp->mg_mode);
-        LAUNCH(s, k_solve_begin, 1, 1, s->d_sc);
+        if (!in_step) LAUNCH(s, k_solve_begin, 1, 1, s->d_sc);
         if (s->variant != 0) { // fused smooth(): 4 colour passes + residual per launch, p ping-ponged
             const int ntx = cdiv(g.nx, RB_TX), nty = cdiv(g.ny, RB_TY);
             for (int vc = 0; vc < pp->vcycles; ++vc) {
@@ -484,15 +666,12 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
                 if (!single) TRY(halo_exchange2(s, s->p, vc == 0 ? s->rhs : nullptr, RB_HY, HALO_BOTH));
                 if (g.denom_pow2) launch_fused<1>(s, pp->tol, ntx, nty, single);
                 else launch_fused<0>(s, pp->tol, ntx, nty, single);
-                if (!single) {
-                    TRY(allreduce(s, s->d_sc->red, 1, ncclSum));
-                    LAUNCH(s, k_rbgs_fin, 1, 1, s->d_sc, pp->tol);
-                }
+                if (!single) TRY(reduce_fin(s, RED_RBGS, pp->tol, 0));
                 double *t = s->p;
                 s->p = s->p_alt;
                 s->p_alt = t;
             }
-            LAUNCH(s, k_solve_finish, 1, 1, s->d_sc);
+            if (!in_step) LAUNCH(s, k_solve_finish, 1, 1, s->d_sc);
             return 0;
         }
         dim3 cblock(32, 8), cgrid(cdiv(cdiv(g.nx, 2), 32), cdiv(g.ny, 8));
@@ -508,21 +687,18 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp) {
                 }
             if (!single) TRY(halo_exchange2(s, s->p, nullptr, 1, HALO_BOTH));
             LAUNCH(s, k_rbgs_residual, rgrid, 256, g, s->p, s->rhs, s->d_sc, s->partials, pp->tol, single);
-            if (!single) {
-                TRY(allreduce(s, s->d_sc->red, 1, ncclSum));
-                LAUNCH(s, k_rbgs_fin, 1, 1, s->d_sc, pp->tol);
-            }
+            if (!single) TRY(reduce_fin(s, RED_RBGS, pp->tol, 0));
         }
     }
-    LAUNCH(s, k_solve_finish, 1, 1, s->d_sc);
+    if (!in_step) LAUNCH(s, k_solve_finish, 1, 1, s->d_sc);
     return 0;
 }
 
-void enqueue_project(cfd_b200_solver *s, const Scalars *dt_src, double dt_arg, int pin = 1) {
+void enqueue_project(cfd_b200_solver *s, const Scalars *dt_src, double dt_arg, int pin = 1, int fin_solve = 0) {
     const Geom &g = s->g;
     int rpb = 4;
     dim3 grid = row_grid(s, cdiv(g.nx + 1, 2), g.ny + 1, &rpb);
-    LAUNCH(s, k_project, grid, 256, g, s->u, s->v, s->p, dt_src, dt_arg, s->d_sc, rpb, pin);
+    LAUNCH(s, k_project, grid, 256, g, s->u, s->v, s->p, dt_src, dt_arg, s->d_sc, rpb, pin, fin_solve);
 }
 
 // TimeIntegrator::step, time_integrator.cpp:47-239
@@ -555,11 +731,11 @@ int enqueue_step(cfd_b200_solver *s, const cfd_b200_bc *bc_in, double Re, double
     stage_mark(s, ST_DIV);
     enqueue_divergence(s, 1, 1); // :158-186
     stage_mark(s, ST_SOLVE);
-    int rc = enqueue_solve(s, pp); // :187
+    int rc = enqueue_solve(s, pp, true); // :187
     if (rc) return rc;
     TRY(halo_exchange2(s, s->p, nullptr, 1, HALO_UP)); // v faces of the bottom row read p one row below the slab
     stage_mark(s, ST_PROJECT);
-    enqueue_project(s, s->d_sc, 0.0); // :188-202
+    enqueue_project(s, s->d_sc, 0.0, 1, 1); // :188-202 (+ last_residual_ = isfinite(res) ? res : 1e9)
     stage_mark(s, ST_BC3);
     enqueue_bc(s, bc, s->u, s->v, s->p, 1); // :205-207
     TRY(halo_exchange2(s, s->u, s->v, 2, HALO_BOTH)); // v row above for the divergence; everything else for the next step
@@ -567,11 +743,7 @@ int enqueue_step(cfd_b200_solver *s, const cfd_b200_bc *bc_in, double Re, double
     stage_mark(s, ST_DIV2);
     enqueue_divergence(s, 0, 1, 1); // :210-220 (+ max|u|, max|v| for the next step's compute_cfl)
     s->cfl_cached = true;
-    if (s->nranks > 1) { // one collective: CFL maxima of the next step + the two partial sums of squares
-        LAUNCH(s, k_slab_pack, 1, 1, s->d_sc);
-        NCCLCHK(nccl_api().AllGather(s->d_sc->red, s->gathered, 4, ncclDouble, s->comm, s->stream));
-        LAUNCH(s, k_slab_unpack, 1, 1, s->d_sc, s->gathered, s->nranks);
-    }
+    TRY(reduce_fin(s, RED_STEP_END, 0.0, 0)); // CFL maxima of the next step + the two partial sums of squares
     LAUNCH(s, k_sanitize_if, s->sm_count * 4, 256, g, s->p, s->d_sc); // :236
     stage_mark(s, ST_END);
     s->ev_valid = s->profiling != 0;
@@ -674,6 +846,7 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(CFD_B200_EINVAL, "bad rank %d of %d", rank, nranks);
     if (nranks > 1 && !nccl_id128) return fail(CFD_B200_EINVAL, "nccl_id128 is NULL");
     if (nranks > 1 && ny / nranks < 8) return fail(CFD_B200_EINVAL, "need at least 8 cell rows per slab");
+    if (nranks > P2P_MAXR) return fail(CFD_B200_EINVAL, "at most %d row slabs", P2P_MAXR);
     if (nranks > 1 && !nccl_api().load()) return fail(CFD_B200_ECOMM, "NCCL unavailable: %s", nccl_api().error);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -688,6 +861,7 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
     s->Lx = Lx, s->Ly = Ly;
     s->rank = rank;
     s->nranks = nranks;
+    s->pdl = getenv("CFD_B200_PDL") ? atoi(getenv("CFD_B200_PDL")) != 0 : 1;
     int row0 = 0, nrows = ny;
     slab_partition(ny, rank, nranks, &row0, &nrows);
     fill_geom(s->g, nx, ny, Lx, Ly, row0, nrows, rank == 0, rank == nranks - 1);
@@ -697,10 +871,16 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
     int rc = 0;
     do {
         if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(CFD_B200_ECUDA, "stream create failed"); break; }
-        double **fields[] = {&s->u, &s->v, &s->p, &s->p_alt, &s->rhs, &s->u1, &s->v1, &s->r, &s->sA, &s->sB};
-        for (double **f : fields)
-            if ((rc = alloc_field(s, f)) != 0) break;
-        if (rc) break;
+        {   // one arena (a multiple of 2 MiB: its own mapping, one IPC handle): NFIELDS fields + this rank's P2PBlock
+            size_t bytes = NFIELDS * s->n * sizeof(double) + sizeof(P2PBlock);
+            bytes = (bytes + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+            cudaError_t ea = cudaMalloc(&s->arena, bytes);
+            if (ea != cudaSuccess) { rc = fail(ea == cudaErrorMemoryAllocation ? CFD_B200_ENOMEM : CFD_B200_ECUDA, "arena of %zu bytes: %s", bytes, cudaGetErrorString(ea)); break; }
+            if (cudaMemsetAsync(s->arena, 0, bytes, s->stream) != cudaSuccess) { rc = fail(CFD_B200_ECUDA, "arena memset failed"); break; }
+            double **fields[NFIELDS] = {&s->u, &s->v, &s->p, &s->p_alt, &s->rhs, &s->u1, &s->v1, &s->r, &s->sA, &s->sB};
+            for (int k = 0; k < NFIELDS; ++k) *fields[k] = s->arena + (size_t)k * s->n;
+            s->blk[rank] = reinterpret_cast<P2PBlock *>(s->arena + (size_t)NFIELDS * s->n);
+        }
         if (cudaMalloc(&s->d_sc, sizeof(Scalars)) != cudaSuccess) { rc = fail(CFD_B200_ENOMEM, "scalars alloc failed"); break; }
         cudaMemsetAsync(s->d_sc, 0, sizeof(Scalars), s->stream);
         if (cudaMallocHost(&s->h_sc, sizeof(Scalars)) != cudaSuccess) { rc = fail(CFD_B200_ENOMEM, "pinned alloc failed"); break; }
@@ -728,6 +908,7 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
             ncclResult_t r = nccl_api().CommInitRank(&s->comm, nranks, id, rank);
             if (r != ncclSuccess) { rc = fail(CFD_B200_ECOMM, "ncclCommInitRank: %s", nccl_api().GetErrorString(r)); break; }
             if (cudaMalloc(&s->gathered, 4 * nranks * sizeof(double)) != cudaSuccess) { rc = fail(CFD_B200_ENOMEM, "gather buffer"); break; }
+            if ((rc = p2p_setup(s)) != 0) break;
         }
     } while (0);
     if (rc) {
@@ -753,6 +934,7 @@ void cfd_b200_destroy(cfd_b200_solver *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    p2p_teardown(s);
     if (s->comm) nccl_api().CommDestroy(s->comm);
     if (s->gathered) cudaFree(s->gathered);
     if (s->coop_xrows) cudaFree(s->coop_xrows);
@@ -761,7 +943,7 @@ void cfd_b200_destroy(cfd_b200_solver *s) {
         if (s->mg[l].p) cudaFree(s->mg[l].p);
         if (s->mg[l].rhs) cudaFree(s->mg[l].rhs);
     }
-    double *fields[] = {s->u, s->v, s->p, s->p_alt, s->rhs, s->u1, s->v1, s->r, s->sA, s->sB, s->scratch_u, s->scratch_v, s->partials};
+    double *fields[] = {s->arena, s->scratch_u, s->scratch_v, s->partials};
     for (double *f : fields)
         if (f) cudaFree(f);
     if (s->d_sc) cudaFree(s->d_sc);
@@ -849,8 +1031,11 @@ int cfd_b200_sync(cfd_b200_solver *s, cfd_b200_step_info *info) {
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->stream));
     fill_info(s, info);
+    if (s->h_sc->comm_error) return fail(CFD_B200_ECOMM, "rank %d: a peer did not arrive within %d s (peer-memory exchange)", s->rank, (int)(P2P_TIMEOUT_NS / 1000000000ull));
     return 0;
 }
+
+int cfd_b200_comm_mode(const cfd_b200_solver *s) { return !s || s->nranks == 1 ? 0 : (s->p2p_on ? 2 : 1); }
 
 int cfd_b200_step(cfd_b200_solver *s, const cfd_b200_bc *bc, double Re, double CFL, const cfd_b200_params *pp,
                   double dt_override, cfd_b200_step_info *info) {
@@ -870,9 +1055,8 @@ int cfd_b200_divergence_l2(cfd_b200_solver *s, double *out) {
         if (rc) return rc;
     }
     LAUNCH(s, k_diag, grid, 256, g, s->u, s->v, s->d_sc, s->partials);
-    if (s->nranks > 1) {
-        int rc = allreduce(s, &s->d_sc->diag_sum, 1, ncclSum);
-        if (!rc) rc = allreduce(s, &s->d_sc->diag_max_bits, 1, ncclMax);
+    {
+        int rc = reduce_fin(s, RED_DIAG, 0.0, 0);
         if (rc) return rc;
     }
     CU(cudaMemcpyAsync(s->h_sc, s->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s->stream));

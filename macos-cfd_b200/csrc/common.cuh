@@ -72,7 +72,19 @@ struct Scalars {
     unsigned long long diag_max_bits;
     unsigned int ticket[4]; // last-block tickets of the grid reductions
     double red[4];          // row slabs: local partial sums handed to the allreduce, then to the k_*_fin kernels
+    int comm_error;         // a bounded peer wait (p2p.cuh) ran out: the step's results are invalid
+    int pad_;
 };
+
+// Programmatic dependent launch (sm_90+): every kernel of the path starts with pdl_begin().  launch_dependents lets
+// the NEXT kernel of the stream be scheduled as soon as all blocks of this one are resident (its blocks then sit in
+// griddepcontrol.wait), so launch latency and block ramp-up overlap this kernel's tail; wait returns once every
+// predecessor grid has completed and its memory is visible -- nothing before it may touch global memory.
+// Without the launch attribute (CFD_B200_PDL=0, or a non-kernel predecessor) both instructions are no-ops.
+__device__ __forceinline__ void pdl_begin() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Exact restatements of the C++ library calls the reference uses (argument order matters for +-0 / NaN):

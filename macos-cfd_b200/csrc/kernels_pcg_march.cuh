@@ -44,7 +44,7 @@ __device__ __forceinline__ bool pm_setup(const Geom &g, PmGeom &t) {
 // Phase 1: s_new = z + beta*s_old (z = inv_diag*r; first iteration: s_new = z), dot(s_new, L s_new).
 __global__ void __launch_bounds__(32 * PM_WARPS)
     k_pcg_phase1_march(Geom g, const double *__restrict__ r, const double *__restrict__ s_old,
-                       double *__restrict__ s_new, Scalars *sc, double *partials, int RY, int finish) {
+                       double *__restrict__ s_new, Scalars *sc, double *partials, int RY, int finish) { pdl_begin();
     if (sc->done) return;
     PmGeom t;
     double acc[1] = {0.0};
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(32 * PM_WARPS)
 // Phase 2: p += alpha*s, r -= alpha*(L s), pin, dot(r,r), dot(r, inv_diag*r) + the scalar tail.
 __global__ void __launch_bounds__(32 * PM_WARPS)
     k_pcg_phase2_march(Geom g, double *__restrict__ p, double *__restrict__ r, const double *__restrict__ s,
-                       Scalars *sc, double *partials, int RY, double tol, int max_iters, int finish) {
+                       Scalars *sc, double *partials, int RY, double tol, int max_iters, int finish) { pdl_begin();
     if (sc->done) return;
     PmGeom t;
     double acc[2] = {0.0, 0.0};

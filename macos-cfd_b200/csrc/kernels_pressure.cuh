@@ -82,17 +82,17 @@ __device__ __forceinline__ void rbgs_tail(Scalars *sc, double rr, double tol) {
     sc->iters = sc->iters + 1;
     if (res < tol) sc->done = 1;
 }
-__global__ void k_pcg_fin_init(Scalars *sc, double tol, int max_iters) { pcg_tail_init(sc, sc->red[0], sc->red[1], tol, max_iters); }
-__global__ void k_pcg_fin1(Scalars *sc) { if (!sc->done) pcg_tail1(sc, sc->red[0]); }
-__global__ void k_pcg_fin2(Scalars *sc, double tol, int max_iters) { if (!sc->done) pcg_tail2(sc, sc->red[0], sc->red[1], tol, max_iters); }
-__global__ void k_rbgs_fin(Scalars *sc, double tol) { if (!sc->done) rbgs_tail(sc, sc->red[0], tol); }
+__global__ void k_pcg_fin_init(Scalars *sc, double tol, int max_iters) { pdl_begin(); pcg_tail_init(sc, sc->red[0], sc->red[1], tol, max_iters); }
+__global__ void k_pcg_fin1(Scalars *sc) { pdl_begin(); if (!sc->done) pcg_tail1(sc, sc->red[0]); }
+__global__ void k_pcg_fin2(Scalars *sc, double tol, int max_iters) { pdl_begin(); if (!sc->done) pcg_tail2(sc, sc->red[0], sc->red[1], tol, max_iters); }
+__global__ void k_rbgs_fin(Scalars *sc, double tol) { pdl_begin(); if (!sc->done) rbgs_tail(sc, sc->red[0], tol); }
 
 // PCG start (pressure.cpp:133-177): p = 0 everywhere (done by a memset before this kernel), Ap = L(0) = 0,
 // r = fin0(rhs) - 0, rho = dot(r, inv_diag*r), res = sqrt(max(0, dot(r,r))).  z and s are not stored: the
 // first direction update recomputes z = inv_diag*r (flag `first`).
 __global__ void __launch_bounds__(PT_THREADS)
     k_pcg_init(Geom g, const double *__restrict__ rhs, double *__restrict__ r, Scalars *sc, double *partials,
-               double tol, int max_iters, int finish) {
+               double tol, int max_iters, int finish) { pdl_begin();
     double acc[2] = {0.0, 0.0};
     const int c2 = threadIdx.x; // 256 threads = 512 cells per row chunk
     for (int jj = 1 + blockIdx.y; jj <= g.ny; jj += gridDim.y) {
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(PT_THREADS)
 // inputs => same bits), which saves 16 B/cell of HBM traffic per iteration.
 __global__ void __launch_bounds__(PT_THREADS)
     k_pcg_phase1(Geom g, const double *__restrict__ r, const double *__restrict__ s_old, double *__restrict__ s_new,
-                 Scalars *sc, double *partials, int ntx, int ntiles, int finish) {
+                 Scalars *sc, double *partials, int ntx, int ntiles, int finish) { pdl_begin();
     if (sc->done) return;
     __shared__ double sm[(PT_Y + 2) * PT_S];
     const bool first = sc->first != 0;
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(PT_THREADS)
 // scalar tail of the iteration (residual test :202-204, beta :219, loop condition :179) in the last block.
 __global__ void __launch_bounds__(PT_THREADS)
     k_pcg_phase2(Geom g, double *__restrict__ p, double *__restrict__ r, const double *__restrict__ s, Scalars *sc,
-                 double *partials, int ntx, int ntiles, double tol, int max_iters, int finish) {
+                 double *partials, int ntx, int ntiles, double tol, int max_iters, int finish) { pdl_begin();
     if (sc->done) return;
     __shared__ double sm[(PT_Y + 2) * PT_S];
     const double alpha = sc->alpha;
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(PT_THREADS)
 }
 
 // last_residual_ = isfinite(res) ? res : 1e9 (pressure.cpp:123, :232)
-__global__ void k_solve_finish(Scalars *sc) {
+__global__ void k_solve_finish(Scalars *sc) { pdl_begin();
     double res = sc->res;
     if (!finite_d(res)) {
         sc->nonfinite_res = 1;
@@ -295,7 +295,7 @@ __global__ void k_solve_finish(Scalars *sc) {
 // ---------------------------------------------------------------------------------------------------------
 template <int POW2>
 __global__ void __launch_bounds__(256)
-    k_rbgs_colour(Geom g, double *p, const double *__restrict__ rhs, int colour, const Scalars *sc) {
+    k_rbgs_colour(Geom g, double *p, const double *__restrict__ rhs, int colour, const Scalars *sc) { pdl_begin();
     if (sc->done) return;
     const int jj = 1 + blockIdx.y * blockDim.y + threadIdx.y;
     if (jj > g.ny) return;
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(256)
 // the `res < tol` test of the vcycle loop (pressure.cpp:118-122).
 __global__ void __launch_bounds__(256)
     k_rbgs_residual(Geom g, const double *__restrict__ p, const double *__restrict__ rhs, Scalars *sc,
-                    double *partials, double tol, int finish) {
+                    double *partials, double tol, int finish) { pdl_begin();
     if (sc->done) return;
     const int ii = 1 + blockIdx.x * blockDim.x + threadIdx.x;
     double acc[1] = {0.0};
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(256)
     });
 }
 
-__global__ void k_solve_begin(Scalars *sc) {
+__global__ void k_solve_begin(Scalars *sc) { pdl_begin();
     sc->done = 0;
     sc->iters = 0;
     sc->res = 1e9; // "double res = 1e9" (pressure.cpp:117) survives vcycles == 0

@@ -65,7 +65,7 @@ __device__ __forceinline__ void rb_update(const Geom &g, double *sm, int ly, int
 template <int POW2, int PAR0>
 __global__ void __launch_bounds__(RB_THREADS, RB_MINBLOCKS)
     k_rbgs_fused(Geom g, const double *__restrict__ pin, double *__restrict__ pout, const double *__restrict__ rhs,
-                 Scalars *sc, double *partials, double tol, int ntx, int finish) {
+                 Scalars *sc, double *partials, double tol, int ntx, int finish) { pdl_begin();
     extern __shared__ double sm_raw[];
     double *sm = sm_raw + RB_PAD; // [2][RB_H][RB_K], padded on both sides
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

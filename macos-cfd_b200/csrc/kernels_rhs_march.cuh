@@ -73,7 +73,7 @@ __device__ __forceinline__ double shfl_up(double x) { return __shfl_up_sync(0xff
 template <int MODE>
 __global__ void __launch_bounds__(32 * MARCH_WARPS, MARCH_MINBLOCKS)
     k_rhs_march(Geom g, RhsConst k, const double *__restrict__ uin, const double *__restrict__ vin, double *uout,
-                double *vout, Scalars *sc, int XA, int XB, int YA, int YB, int RY) {
+                double *vout, Scalars *sc, int XA, int XB, int YA, int YB, int RY) { pdl_begin();
     const int lane = threadIdx.x & 31;
     const int wx = blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
     const int X0 = XA - 2 + MARCH_COLS * wx; // raw column of lane 0's first column (odd => aligned double2)

@@ -57,7 +57,7 @@ __device__ __forceinline__ void bc_row(double *row, int cR, bool both, int ltype
 
 // Row slabs: the pass also covers the 2 halo rows towards a neighbouring slab.  It is row-local, so this reproduces
 // exactly what the neighbour does to its own rows and the halo rows stay current without an exchange.
-__global__ void k_bc_lr(Geom g, BcD bc, double *u, double *v, double *p, int sanitize, Scalars *sc) {
+__global__ void k_bc_lr(Geom g, BcD bc, double *u, double *v, double *p, int sanitize, Scalars *sc) { pdl_begin();
     const int jlo = g.bottom ? 1 : -1;
     int jj = blockIdx.x * blockDim.x + threadIdx.x + jlo;
     int flag = 0;
@@ -105,7 +105,7 @@ __device__ __forceinline__ void bc_col(double *col, size_t P, int rT, bool both,
     }
 }
 
-__global__ void k_bc_bt(Geom g, BcD bc, double *u, double *v, double *p, int sanitize, Scalars *sc) {
+__global__ void k_bc_bt(Geom g, BcD bc, double *u, double *v, double *p, int sanitize, Scalars *sc) { pdl_begin();
     int ii = blockIdx.x * blockDim.x + threadIdx.x; // raw column 0 .. nx+2
     int flag = 0;
     bool both = bc.bottom.type == BC_PERIODIC && bc.top.type == BC_PERIODIC;
@@ -150,7 +150,7 @@ __global__ void k_bc_bt(Geom g, BcD bc, double *u, double *v, double *p, int san
 // =========================================================================================================
 
 // max |q| over the faces ii in [1,IX], jj in [1,JY]; block = 256 threads = 512 columns as double2
-__global__ void k_absmax(Geom g, const double *__restrict__ u, const double *__restrict__ v, Scalars *sc) {
+__global__ void k_absmax(Geom g, const double *__restrict__ u, const double *__restrict__ v, Scalars *sc) { pdl_begin();
     const int c2 = blockIdx.x * blockDim.x + threadIdx.x; // double2 index along the pitch
     const int ii = 2 * c2 - CFD_XOFF;                     // raw column of .x; .y is ii+1
     double mu = 0.0, mv = 0.0;
@@ -173,7 +173,7 @@ __global__ void k_absmax(Geom g, const double *__restrict__ u, const double *__r
 }
 
 // One thread: dt from umax/vmax exactly as the host code does, and reset of the per-step accumulators.
-__global__ void k_dt(Geom g, double Re, double CFL, double dt_override, Scalars *sc, int cfl_only) {
+__global__ void k_dt(Geom g, double Re, double CFL, double dt_override, Scalars *sc, int cfl_only) { pdl_begin();
     double umax = __longlong_as_double((long long)sc->umax_bits);
     double vmax = __longlong_as_double((long long)sc->vmax_bits);
     sc->umax_bits = 0ull;
@@ -204,6 +204,8 @@ __global__ void k_dt(Geom g, double Re, double CFL, double dt_override, Scalars 
     sc->nonfinite_res = 0;
     sc->breakdown_iter = -1;
     sc->iters = 0;
+    sc->done = 0;  // k_solve_begin's part (pressure.cpp:117): "double res = 1e9" survives vcycles == 0
+    sc->res = 1e9;
 }
 
 // =========================================================================================================
@@ -238,7 +240,7 @@ struct RhsConst {
 
 // diffuse_u / diffuse_v as free functions (diffusion.cpp:5-39): out += invRe * laplacian(q) on the advection
 // interior set ii in [2, IX-1], jj in [2, JY-1]; nothing else is touched.
-__global__ void k_diffuse_add(Geom g, const double *__restrict__ q, double *out, double invRe, int IX, int JY) {
+__global__ void k_diffuse_add(Geom g, const double *__restrict__ q, double *out, double invRe, int IX, int JY) { pdl_begin();
     const int ii = 2 + blockIdx.x * blockDim.x + threadIdx.x, jj = 2 + blockIdx.y;
     if (ii > IX - 1 || jj > JY - 1) return;
     const size_t o = gidx(g, ii, jj);
@@ -293,7 +295,7 @@ struct RhsRects {
 template <int MODE>
 __global__ void __launch_bounds__(RHS_TX *RHS_TY)
     k_rhs_simple(Geom g, RhsConst k, const double *__restrict__ uin, const double *__restrict__ vin, double *uout,
-                 double *vout, Scalars *sc, RhsRects rc) {
+                 double *vout, Scalars *sc, RhsRects rc) { pdl_begin();
     constexpr int S = RHS_TX + 4 + 1; // +1: odd stride
     __shared__ double us[(RHS_TY + 4) * S], vs[(RHS_TY + 4) * S];
     int rk = 0, first = 0;
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(RHS_TX *RHS_TY)
 template <int PRE>
 __global__ void __launch_bounds__(256)
     k_divergence(Geom g, const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ rhs,
-                 double *p, Scalars *sc, double *partials, int want_sum, int rpb, int want_max) {
+                 double *p, Scalars *sc, double *partials, int want_sum, int rpb, int want_max) { pdl_begin();
     const int ii = 1 + blockIdx.x * blockDim.x + threadIdx.x;
     double acc[1] = {0.0};
     double mu = 0.0, mv = 0.0; // max |u|, max |v| over all faces (compute_cfl of the NEXT step, metrics.cpp:8-24)
@@ -405,7 +407,14 @@ __global__ void __launch_bounds__(256)
 // =========================================================================================================
 __global__ void __launch_bounds__(256)
     k_project(Geom g, double *__restrict__ u, double *__restrict__ v, double *p, const Scalars *sc, double dt_arg,
-              Scalars *flags, int rpb, int pin) {
+              Scalars *flags, int rpb, int pin, int fin_solve) { pdl_begin();
+    if (fin_solve && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        const double res = flags->res; // last_residual_ = isfinite(res) ? res : 1e9 (pressure.cpp:123, :232)
+        if (!finite_d(res)) {
+            flags->nonfinite_res = 1;
+            flags->res = 1e9;
+        }
+    }
     // One thread = two adjacent columns (aligned double2) marching up rpb rows; the p pair of the row below is
     // carried in registers, p(ii-1) comes from the left lane.
     const int ii = 1 + 2 * (blockIdx.x * blockDim.x + threadIdx.x);
@@ -465,13 +474,13 @@ __global__ void __launch_bounds__(256)
 }
 
 // Row slabs, end of a step: one all-gather carries what compute_cfl of the NEXT step and the divergence log need.
-__global__ void k_slab_pack(Scalars *sc) {
+__global__ void k_slab_pack(Scalars *sc) { pdl_begin();
     sc->red[0] = __longlong_as_double((long long)sc->umax_bits);
     sc->red[1] = __longlong_as_double((long long)sc->vmax_bits);
     sc->red[2] = sc->div_before; // partial sums of squares
     sc->red[3] = sc->div_after;
 }
-__global__ void k_slab_unpack(Scalars *sc, const double *gathered, int nranks) {
+__global__ void k_slab_unpack(Scalars *sc, const double *gathered, int nranks) { pdl_begin();
     double um = 0.0, vm = 0.0, db = 0.0, da = 0.0;
     for (int r = 0; r < nranks; ++r) { // fixed rank order: identical on every rank
         um = max2(um, gathered[4 * r]);
@@ -486,7 +495,7 @@ __global__ void k_slab_unpack(Scalars *sc, const double *gathered, int nranks) {
 }
 
 // sanitize_field(s.p) (time_integrator.cpp:236); only does work when the solver flagged a non-finite p
-__global__ void k_sanitize_if(Geom g, double *a, Scalars *sc) {
+__global__ void k_sanitize_if(Geom g, double *a, Scalars *sc) { pdl_begin();
     if (!sc->nonfinite_p) return;
     size_t n = (size_t)g.P * g.rows;
     int flag = 0;
@@ -499,7 +508,7 @@ __global__ void k_sanitize_if(Geom g, double *a, Scalars *sc) {
 // Driver diagnostics: divergence_l2 (metrics.cpp:68-86) and max_velocity (metrics.cpp:52-66)
 // =========================================================================================================
 __global__ void __launch_bounds__(256)
-    k_diag(Geom g, const double *__restrict__ u, const double *__restrict__ v, Scalars *sc, double *partials) {
+    k_diag(Geom g, const double *__restrict__ u, const double *__restrict__ v, Scalars *sc, double *partials) { pdl_begin();
     const int ii = 1 + blockIdx.x * blockDim.x + threadIdx.x;
     double acc[1] = {0.0};
     double m = 0.0;

@@ -26,7 +26,7 @@ __device__ __forceinline__ double mg_wall(int nx, int ny, double idx2, double id
 }
 
 // ---------------------------------------------------------------- generic (any level) global-memory kernels
-__global__ void k_mg_zero_ghosts(MgLevel L, const Scalars *sc) {
+__global__ void k_mg_zero_ghosts(MgLevel L, const Scalars *sc) { pdl_begin();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t <= L.nx + 1) {
         L.p[mg_idx(L, t, 0)] = 0.0;
@@ -38,7 +38,7 @@ __global__ void k_mg_zero_ghosts(MgLevel L, const Scalars *sc) {
     }
 }
 
-__global__ void __launch_bounds__(256) k_mg_colour(MgLevel L, int colour, const Scalars *sc) {
+__global__ void __launch_bounds__(256) k_mg_colour(MgLevel L, int colour, const Scalars *sc) { pdl_begin();
     if (sc->done) return;
     const int jj = 1 + blockIdx.y * blockDim.y + threadIdx.y;
     if (jj > L.ny) return;
@@ -59,7 +59,7 @@ __device__ __forceinline__ double mg_resid(const MgLevel &L, int ii, int jj) {
 }
 
 // residual of the fine level + restriction to the coarse right-hand side + coarse initial guess 0, fused
-__global__ void __launch_bounds__(256) k_mg_restrict(MgLevel F, MgLevel C, const Scalars *sc) {
+__global__ void __launch_bounds__(256) k_mg_restrict(MgLevel F, MgLevel C, const Scalars *sc) { pdl_begin();
     if (sc->done) return;
     const int I = 1 + blockIdx.x * blockDim.x + threadIdx.x, J = 1 + blockIdx.y * blockDim.y + threadIdx.y;
     if (I > C.nx || J > C.ny) return;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) k_mg_restrict(MgLevel F, MgLevel C, const
 }
 
 // bilinear prolongation + correction, fused
-__global__ void __launch_bounds__(256) k_mg_prolong(MgLevel F, MgLevel C, const Scalars *sc) {
+__global__ void __launch_bounds__(256) k_mg_prolong(MgLevel F, MgLevel C, const Scalars *sc) { pdl_begin();
     if (sc->done) return;
     const int ii = 1 + blockIdx.x * blockDim.x + threadIdx.x, jj = 1 + blockIdx.y * blockDim.y + threadIdx.y;
     if (ii > F.nx || jj > F.ny) return;
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) k_mg_prolong(MgLevel F, MgLevel C, const 
 }
 
 // ||rhs - L p||_2 of the fine level after a cycle, and the cycle loop's exit test
-__global__ void __launch_bounds__(256) k_mg_residual_norm(MgLevel L, Scalars *sc, double *partials, double tol) {
+__global__ void __launch_bounds__(256) k_mg_residual_norm(MgLevel L, Scalars *sc, double *partials, double tol) { pdl_begin();
     if (sc->done) return;
     const int ii = 1 + blockIdx.x * blockDim.x + threadIdx.x;
     double acc[1] = {0.0};
@@ -135,7 +135,7 @@ __device__ __forceinline__ double cta_resid(const double *p, const double *rhs, 
     return rhs[jj * S + ii] - Ap;
 }
 
-__global__ void __launch_bounds__(1024) k_mg_coarse_cta(MgLevel G, MgCtaPlan plan, const Scalars *sc) {
+__global__ void __launch_bounds__(1024) k_mg_coarse_cta(MgLevel G, MgCtaPlan plan, const Scalars *sc) { pdl_begin();
     if (sc->done) return;
     extern __shared__ double smg[];
     auto P = [&](int l) { return smg + plan.off[l]; };

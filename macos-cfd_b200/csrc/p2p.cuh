@@ -1,0 +1,183 @@
+// p2p.cuh -- row-slab communication straight over NVLink 5 / NVSwitch peer memory (one process per GPU, CUDA IPC).
+//
+// Every message of the slab decomposition is tiny -- a few rows to the two neighbours, or 1-4 doubles
+// to everybody -- so what matters is latency, not bandwidth.  An NCCL send/recv group or a 2-double allreduce costs
+// ~25-35 us per call on 8 GPUs; the kernels here do the same work in one launch each with plain stores into the peer's
+// memory and flag words for ordering (a few us):
+//
+//   k_halo_xchg   handshake ("I have entered exchange #e": everything that reads or writes my halo rows before this
+//                 point of my stream is done) -> wait for the neighbour's handshake -> store my edge rows into the
+//                 neighbour's halo rows -> fence -> data flag -> wait for the neighbour's data flag.
+//   k_p2p_reduce  the allreduce / all-gather of the PCG dots, the smoother residual, the CFL maxima and the divergence
+//                 sums FUSED with the scalar tail that consumes them: every rank stores its partial into slot [rank] of
+//                 every peer, waits for all slots of its own block and adds them in rank order, so all ranks compute
+//                 bit-identical totals (and therefore take identical decisions) without any library call.
+//
+// All flags are monotonically increasing 64-bit epochs with a single writer; nothing is ever reset, so there is no
+// ABA window.  The reduce slots are double-buffered on the epoch parity: a rank can be at most one reduce ahead of the
+// slowest one (it needs everybody's contribution to pass the next).  Waits are bounded (P2P_TIMEOUT_NS): a peer that
+// never arrives sets Scalars::comm_error instead of hanging the GPU, and cfd_b200_sync reports CFD_B200_ECOMM.
+//
+// NCCL (comm.cuh) stays the bootstrap (handle exchange, agreement that every rank mapped its peers) and the fallback
+// when peer mapping is not possible.
+#pragma once
+#include "common.cuh"
+
+#define P2P_MAXR 16
+#define P2P_TIMEOUT_NS 20000000000ull // 20 s
+#define P2P_MAGIC 0xCFDB200000000000ull
+
+struct P2PBlock {
+    unsigned long long magic;               // P2P_MAGIC + rank: checked through the mapping before it is trusted
+    unsigned long long enter_flag[2];       // [0] written by the slab below, [1] by the slab above
+    unsigned long long data_flag[2];
+    unsigned long long red_flag[2][P2P_MAXR]; // [epoch parity][source rank]
+    double red_val[2][P2P_MAXR][4];
+    unsigned int ticket;
+    unsigned int pad;
+};
+
+__device__ __forceinline__ unsigned long long p2p_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void p2p_signal(unsigned long long *flag, unsigned long long epoch) {
+    __threadfence_system(); // everything this thread has observed or written is visible before the flag
+    *reinterpret_cast<volatile unsigned long long *>(flag) = epoch;
+}
+__device__ __forceinline__ bool p2p_wait(const unsigned long long *flag, unsigned long long epoch, Scalars *sc) {
+    const volatile unsigned long long *f = flag;
+    bool ok = true;
+    if (*f < epoch) {
+        const unsigned long long t0 = p2p_now();
+        while (*f < epoch) {
+            if (*reinterpret_cast<volatile int *>(&sc->comm_error) || p2p_now() - t0 > P2P_TIMEOUT_NS) {
+                sc->comm_error = 1;
+                ok = false;
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+    return ok;
+}
+
+struct HaloJob {
+    const double *src; // my rows
+    double *dst;       // the neighbour's halo rows (peer memory)
+    int nb;            // 0 = slab below, 1 = slab above
+};
+struct HaloArgs {
+    HaloJob job[4];
+    int njobs;
+    unsigned long long count; // doubles per job (whole rows: a multiple of 16)
+    unsigned long long *peer_enter[2], *peer_data[2]; // the neighbours' flag words I write (NULL: no neighbour there)
+    unsigned long long epoch;
+};
+
+__global__ void __launch_bounds__(256) k_halo_xchg(HaloArgs a, P2PBlock *me, Scalars *sc) { pdl_begin();
+    __shared__ int s_go, s_last;
+    const int tid = threadIdx.x;
+    // 1. handshake: the neighbour may write into my halo rows from now on, and I into its rows once it says the same
+    if (tid < 2) {
+        if (blockIdx.x == 0 && a.peer_enter[tid]) p2p_signal(a.peer_enter[tid], a.epoch);
+        bool ok = true;
+        if (a.peer_enter[tid]) ok = p2p_wait(&me->enter_flag[tid], a.epoch, sc);
+        if (tid == 0) s_go = 1;
+        __syncwarp(0x3);
+        if (!ok) s_go = 0;
+    }
+    __syncthreads();
+    // 2. my edge rows -> the neighbours' halo rows (16-byte stores over NVLink)
+    if (s_go) {
+        const size_t n2 = a.count / 2;
+        for (int j = 0; j < a.njobs; ++j) {
+            const double2 *src = reinterpret_cast<const double2 *>(a.job[j].src);
+            double2 *dst = reinterpret_cast<double2 *>(a.job[j].dst);
+            for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < n2; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&me->ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    // 3. the last block: all rows of all blocks are out -> data flags, then wait for the neighbours' rows
+    if (tid < 2 && a.peer_data[tid]) {
+        p2p_signal(a.peer_data[tid], a.epoch);
+        p2p_wait(&me->data_flag[tid], a.epoch, sc);
+    }
+    if (tid == 0) me->ticket = 0u;
+}
+
+// ---- reductions fused with their scalar tails ------------------------------------------------------------------
+enum {
+    RED_PCG_INIT = 0, // 2 sums  -> pcg_tail_init
+    RED_PCG1,         // 1 sum   -> pcg_tail1
+    RED_PCG2,         // 2 sums  -> pcg_tail2
+    RED_RBGS,         // 1 sum   -> rbgs_tail
+    RED_STEP_END,     // max|u|, max|v|, sum div^2 before / after (end of a step)
+    RED_CFL,          // max|u|, max|v| (compute_cfl after an upload)
+    RED_DIAG          // divergence_l2 sum + max_velocity max
+};
+struct RedArgs {
+    P2PBlock *blk[P2P_MAXR]; // every rank's block (blk[rank] = mine)
+    int nranks, rank, kind;
+    unsigned long long epoch;
+    double tol;
+    int max_iters;
+};
+
+__global__ void __launch_bounds__(32) k_p2p_reduce(RedArgs a, Scalars *sc) { pdl_begin();
+    const int t = threadIdx.x, par = (int)(a.epoch & 1ull);
+    P2PBlock *me = a.blk[a.rank];
+    double v0, v1, v2 = 0.0, v3 = 0.0;
+    switch (a.kind) { // every lane reads the same few words; lanes < nranks forward them
+    case RED_STEP_END:
+        v2 = sc->div_before, v3 = sc->div_after; // partial sums of squares
+        // fallthrough
+    case RED_CFL:
+        v0 = __longlong_as_double((long long)sc->umax_bits), v1 = __longlong_as_double((long long)sc->vmax_bits);
+        break;
+    case RED_DIAG:
+        v0 = sc->diag_sum, v1 = __longlong_as_double((long long)sc->diag_max_bits);
+        break;
+    default:
+        v0 = sc->red[0], v1 = sc->red[1];
+    }
+    if (t < a.nranks) {
+        P2PBlock *dst = a.blk[t];
+        volatile double *slot = dst->red_val[par][a.rank];
+        slot[0] = v0, slot[1] = v1, slot[2] = v2, slot[3] = v3;
+        p2p_signal(&dst->red_flag[par][a.rank], a.epoch);
+        p2p_wait(&me->red_flag[par][t], a.epoch, sc);
+    }
+    __syncthreads();
+    if (t != 0) return;
+    const bool is_max0 = a.kind == RED_STEP_END || a.kind == RED_CFL, is_max1 = is_max0 || a.kind == RED_DIAG;
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+    for (int r = 0; r < a.nranks; ++r) { // fixed rank order: bit-identical on every rank
+        const volatile double *slot = me->red_val[par][r];
+        const double x0 = slot[0], x1 = slot[1];
+        r0 = is_max0 ? max2(r0, x0) : r0 + x0;
+        r1 = is_max1 ? max2(r1, x1) : r1 + x1;
+        r2 += slot[2];
+        r3 += slot[3];
+    }
+    switch (a.kind) {
+    case RED_PCG_INIT: pcg_tail_init(sc, r0, r1, a.tol, a.max_iters); break;
+    case RED_PCG1: if (!sc->done) pcg_tail1(sc, r0); break;
+    case RED_PCG2: if (!sc->done) pcg_tail2(sc, r0, r1, a.tol, a.max_iters); break;
+    case RED_RBGS: if (!sc->done) rbgs_tail(sc, r0, a.tol); break;
+    case RED_STEP_END:
+        sc->div_before = r2, sc->div_after = r3;
+        // fallthrough
+    case RED_CFL:
+        sc->umax_bits = (unsigned long long)__double_as_longlong(r0), sc->vmax_bits = (unsigned long long)__double_as_longlong(r1);
+        break;
+    case RED_DIAG:
+        sc->diag_sum = r0, sc->diag_max_bits = (unsigned long long)__double_as_longlong(r1);
+        break;
+    }
+}

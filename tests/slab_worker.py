@@ -32,8 +32,10 @@ def main():
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--vcycles", type=int, default=2)
     ap.add_argument("--variant", type=int, default=1)
+    ap.add_argument("--p2p", type=int, default=1)  # 0: force the NCCL path (CFD_B200_P2P=0)
     ap.add_argument("--out", required=True)
     a = ap.parse_args()
+    os.environ["CFD_B200_P2P"] = str(a.p2p)
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     dist.init_process_group("gloo")  # CPU plumbing only: the id broadcast and the final gather
@@ -62,7 +64,7 @@ def main():
     dist.gather_object(part, parts if rank == 0 else None, dst=0)
     if rank == 0:
         out = {k: np.concatenate([q[k] for q in parts], axis=0) for k in ("u", "v", "p", "rhs")}
-        np.savez(a.out, hist=np.array(hist), div_l2=div_l2, vmax=vmax, **out)
+        np.savez(a.out, hist=np.array(hist), div_l2=div_l2, vmax=vmax, comm_mode=s.comm_mode, **out)
     s.close()
     dist.destroy_process_group()
 
