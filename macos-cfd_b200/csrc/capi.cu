@@ -18,6 +18,7 @@
 #include "kernels_step.cuh"
 #include "kernels_rhs_march.cuh"
 #include "kernels_rbgs_fused.cuh"
+#include "kernels_rbgs_stream.cuh"
 #include "kernels_vcycle.cuh"
 #include "kernels_pcg_march.cuh"
 #include "kernels_pcg_coop.cuh"
@@ -68,7 +69,7 @@ struct cfd_b200_solver {
     cudaStream_t stream = nullptr;
     long long launches = 0;
     int variant = 1;
-    int pdl = 1; // programmatic dependent launch between consecutive kernels (CFD_B200_PDL=0 turns it off)
+    int pdl = 3; // programmatic dependent launch between consecutive kernels (bit mask, see cfd_b200_create_slab; CFD_B200_PDL=0 turns it off)
     bool cfl_cached = false;   // umax/vmax of the current device State are already in d_sc (from the last step)
     cfd_b200_bc last_bc{};
     int profiling = 0;
@@ -98,15 +99,19 @@ namespace {
 
 // Every kernel launch of the path: programmatic stream serialization (see pdl_begin(), common.cuh) unless disabled.
 template <class... KArgs, class... Args>
-inline void launch_k(cfd_b200_solver *s, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args) {
+inline void launch_kp(cfd_b200_solver *s, int pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at, cfg.numAttrs = s->pdl ? 1 : 0;
+    cfg.attrs = at, cfg.numAttrs = pdl ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
     s->launches++;
+}
+template <class... KArgs, class... Args>
+inline void launch_k(cfd_b200_solver *s, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args) {
+    launch_kp(s, s->pdl & 1, kernel, grid, block, smem, static_cast<Args &&>(args)...);
 }
 #define LAUNCH(s, kernel, grid, block, ...) launch_k(s, kernel, dim3(grid), dim3(block), 0, __VA_ARGS__)
 
@@ -472,12 +477,44 @@ int reduce_fin(cfd_b200_solver *s, int kind, double tol, int max_iters) {
 }
 
 template <int POW2>
-void launch_fused(cfd_b200_solver *s, double tol, int ntx, int nty, int finish) {
+void launch_fused(cfd_b200_solver *s, double tol, int ntx, int nty, int finish, int only_if_redo) {
     const Geom &g = s->g;
+    const int ntiles = ntx * nty;
+    // stand-alone: one block per tile.  As the slow path of the streaming smoother: two blocks per SM walking over the
+    // tiles, so that the launch costs next to nothing when there is nothing to redo.
+    const int grid = only_if_redo && ntiles > 2 * s->sm_count ? 2 * s->sm_count : ntiles;
     if ((1 + g.j0) & 1)
-        launch_k(s, k_rbgs_fused<POW2, 1>, dim3(ntx * nty), dim3(RB_THREADS), RB_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, ntx, finish);
+        launch_kp(s, only_if_redo ? (s->pdl >> 2) & 1 : s->pdl & 1, k_rbgs_fused<POW2, 1>, dim3(grid), dim3(RB_THREADS), RB_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, ntx, ntiles, finish, only_if_redo);
     else
-        launch_k(s, k_rbgs_fused<POW2, 0>, dim3(ntx * nty), dim3(RB_THREADS), RB_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, ntx, finish);
+        launch_kp(s, only_if_redo ? (s->pdl >> 2) & 1 : s->pdl & 1, k_rbgs_fused<POW2, 0>, dim3(grid), dim3(RB_THREADS), RB_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, ntx, ntiles, finish, only_if_redo);
+}
+
+// One smooth() (pressure.cpp:64-111), p -> p_alt.  variant 1: the streaming kernel with the guarded tile kernel behind it
+// as its slow path (a no-op unless a non-finite value turned up); variant 2: the tile kernel alone.
+void enqueue_smooth(cfd_b200_solver *s, double tol, int finish) {
+    const Geom &g = s->g;
+    const int ntx = cdiv(g.nx, RB_TX), nty = cdiv(g.ny, RB_TY);
+    bool stream = s->variant == 1;
+    if (stream) {
+        static const int ry_env = getenv("CFD_B200_RB_RY") ? atoi(getenv("CFD_B200_RB_RY")) : 0;
+        const int nstrips = cdiv(g.nx + 1, RS_OUT), gx = cdiv(nstrips, RS_WARPS);
+        const int nrows = (g.top ? g.ny + 1 : g.ny) - (g.bottom ? 0 : 1) + 1;
+        // Rows per strip: 16 m + 1, so that the RY + 15 steps of a strip are whole turns of the 16-row ring.  15 rows of
+        // pipeline fill per strip: 257 on grids that fill the GPU (B200, 8192^2: RY 129 / 257 / 513 -> 0.46 / 0.42 / 0.50 ms
+        // per smooth), shorter strips to give every SM its 6 blocks, and when even 65-row strips leave SMs empty the
+        // tile kernel is the better one (1024^2: 21 us per smooth against 25).
+        int RY = 257;
+        while (RY > 65 && (long long)gx * cdiv(nrows, RY) < 6LL * s->sm_count) RY = (RY - 1) / 2 + 1;
+        if (ry_env > 0) RY = ry_env;
+        const dim3 grid(gx, cdiv(nrows, RY));
+        if (ry_env <= 0 && (long long)grid.x * grid.y < 3LL * s->sm_count) stream = false;
+        else if (g.denom_pow2)
+            launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<1>, grid, dim3(32 * RS_WARPS), RS_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, RY, nstrips, finish);
+        else
+            launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<0>, grid, dim3(32 * RS_WARPS), RS_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, RY, nstrips, finish);
+    }
+    if (g.denom_pow2) launch_fused<1>(s, tol, ntx, nty, finish, stream);
+    else launch_fused<0>(s, tol, ntx, nty, finish, stream);
 }
 
 // ---- EXTENSION: true geometric V-cycle (kernels_vcycle.cuh; algorithm = the CPU restatement cfd_vcycle.c of the test tree; parity unpinned) ----
@@ -660,12 +697,10 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp, bool in_step = 
         if (pp->mg_mode != CFD_B200_MG_REFERENCE) return fail(CFD_B200_EINVAL, "bad mg_mode %d", pp->mg_mode);
         if (!in_step) LAUNCH(s, k_solve_begin, 1, 1, s->d_sc);
         if (s->variant != 0) { // fused smooth(): 4 colour passes + residual per launch, p ping-ponged
-            const int ntx = cdiv(g.nx, RB_TX), nty = cdiv(g.ny, RB_TY);
             for (int vc = 0; vc < pp->vcycles; ++vc) {
                 // 5 rows of p (and, once, of rhs: it is constant during the solve) for the redundant compute
                 if (!single) TRY(halo_exchange2(s, s->p, vc == 0 ? s->rhs : nullptr, RB_HY, HALO_BOTH));
-                if (g.denom_pow2) launch_fused<1>(s, pp->tol, ntx, nty, single);
-                else launch_fused<0>(s, pp->tol, ntx, nty, single);
+                enqueue_smooth(s, pp->tol, single);
                 if (!single) TRY(reduce_fin(s, RED_RBGS, pp->tol, 0));
                 double *t = s->p;
                 s->p = s->p_alt;
@@ -861,7 +896,10 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
     s->Lx = Lx, s->Ly = Ly;
     s->rank = rank;
     s->nranks = nranks;
-    s->pdl = getenv("CFD_B200_PDL") ? atoi(getenv("CFD_B200_PDL")) != 0 : 1;
+    s->pdl = getenv("CFD_B200_PDL") ? atoi(getenv("CFD_B200_PDL")) : 3;
+    // bit 0: all kernels, bit 1: k_rbgs_stream, bit 2: its slow path.  Bit 2 stays off: measured on B200 at 8192^2, the
+    // (normally idle) slow-path blocks become resident while the streaming kernel is still running and take two 64 KB
+    // shared-memory slots per SM from it: 3.49 ms per step against 3.27.
     int row0 = 0, nrows = ny;
     slab_partition(ny, rank, nranks, &row0, &nrows);
     fill_geom(s->g, nx, ny, Lx, Ly, row0, nrows, rank == 0, rank == nranks - 1);
@@ -897,6 +935,8 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
             rc = fail(CFD_B200_ECUDA, "cudaFuncSetAttribute(k_rbgs_fused) failed: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }
+        cudaFuncSetAttribute(k_rbgs_stream<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_rbgs_stream<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (cudaMalloc(&s->partials, s->partials_n * sizeof(double)) != cudaSuccess) { rc = fail(CFD_B200_ENOMEM, "partials alloc failed"); break; }
         for (int i = 0; i < ST_COUNT; ++i)
             if (cudaEventCreate(&s->ev[i]) != cudaSuccess) { rc = fail(CFD_B200_ECUDA, "event create failed"); break; }

@@ -73,7 +73,7 @@ struct Scalars {
     unsigned int ticket[4]; // last-block tickets of the grid reductions
     double red[4];          // row slabs: local partial sums handed to the allreduce, then to the k_*_fin kernels
     int comm_error;         // a bounded peer wait (p2p.cuh) ran out: the step's results are invalid
-    int pad_;
+    int rb_redo;            // k_rbgs_stream met a non-finite value: the guarded tile kernel redoes this smooth()
 };
 
 // Programmatic dependent launch (sm_90+): every kernel of the path starts with pdl_begin().  launch_dependents lets

@@ -65,16 +65,21 @@ __device__ __forceinline__ void rb_update(const Geom &g, double *sm, int ly, int
 template <int POW2, int PAR0>
 __global__ void __launch_bounds__(RB_THREADS, RB_MINBLOCKS)
     k_rbgs_fused(Geom g, const double *__restrict__ pin, double *__restrict__ pout, const double *__restrict__ rhs,
-                 Scalars *sc, double *partials, double tol, int ntx, int finish) { pdl_begin();
+                 Scalars *sc, double *partials, double tol, int ntx, int ntiles, int finish, int only_if_redo) { pdl_begin();
+    // Launched behind k_rbgs_stream as its guarded slow path: nothing to do unless that kernel met a non-finite value.
+    if (only_if_redo && !*reinterpret_cast<volatile int *>(&sc->rb_redo)) return;
     extern __shared__ double sm_raw[];
     double *sm = sm_raw + RB_PAD; // [2][RB_H][RB_K], padded on both sides
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ty = blockIdx.x / ntx, tx = blockIdx.x - ty * ntx;
-    const int X0 = 1 + tx * RB_TX, Y0 = 1 + ty * RB_TY; // first output cell (raw)
-    const int Xe = X0 - RB_HX, Ye = Y0 - RB_HY;         // raw index of local (0,0)
     const bool done = sc->done != 0;                    // converged earlier: only carry p over to the other buffer
     double acc[1] = {0.0};
     int pflag = 0;
+    // One tile per block when launched with ntiles blocks (the stand-alone smoother); as the slow path behind
+    // k_rbgs_stream the grid is two blocks per SM and each block walks over its tiles.
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int ty = tile / ntx, tx = tile - ty * ntx;
+    const int X0 = 1 + tx * RB_TX, Y0 = 1 + ty * RB_TY; // first output cell (raw)
+    const int Xe = X0 - RB_HX, Ye = Y0 - RB_HY;         // raw index of local (0,0)
 
     // ---- load: thread (warp, lane) owns slots (ly = 4*warp + m, k = lane + 32 n), m < 4, n < 2; a slot is the
     //      aligned pair of local columns (2k, 2k+1).  rhs stays in registers for all passes; mg = margin of a point:
@@ -133,7 +138,7 @@ __global__ void __launch_bounds__(RB_THREADS, RB_MINBLOCKS)
             rv[m][n][1] = fin0(rr.y);
         }
     }
-    if (done) return;
+    if (done) continue;
     __syncthreads();
 
     // ---- four colour passes (pressure.cpp:70-94): pass ps updates colour ps & 1 = class (ps & 1) ^ PAR0, i.e. in
@@ -180,8 +185,12 @@ __global__ void __launch_bounds__(RB_THREADS, RB_MINBLOCKS)
             }
         }
     }
+    __syncthreads(); // the next tile overwrites the shared tile
+    } // tiles
+    if (done) return;
     if (pflag) sc->nonfinite_p = 1;
     grid_sum<1>(acc, partials, &sc->ticket[2], [=](double(&t)[1]) {
+        sc->rb_redo = 0;
         if (finish) rbgs_tail(sc, t[0], tol); // vcycle loop exit, pressure.cpp:120
         else sc->red[0] = t[0];
     });

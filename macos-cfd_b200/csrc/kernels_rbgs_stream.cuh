@@ -1,0 +1,210 @@
+// kernels_rbgs_stream.cuh -- PressureSolver::smooth (pressure.cpp:64-111) as ONE streaming kernel: every warp marches up
+// its own 64-column strip with the four colour passes and the residual following each other two rows apart.
+//
+// Why (ncu on the tile kernel k_rbgs_fused, profiles/r01_*): it reaches the traffic floor (24 B/cell) but runs at 39 %
+// issue utilisation -- 144 instructions per cell, block-wide barriers between passes, a load phase nobody overlaps.
+// Here
+//   * a warp owns columns [X0, X0+64) (52 of them are output, 6 on either side are halo that is recomputed) and keeps
+//     a ring of the last 16 rows of p and rhs in shared memory, private to the warp: no block barrier anywhere, one
+//     __syncwarp per row;
+//   * rows arrive through cp.async four rows ahead of their use (no registers, no stall on the load; plain loads into
+//     registers were measured: they serialise on the scoreboard and stall every step);
+//   * at the step that makes row L available, pass k (k = 0..3) updates its colour in row L-1-2k and the residual is
+//     taken in row L-9.  With two rows between consecutive passes the four updates of a step touch disjoint rows and
+//     are independent of each other (the rows a pass writes, L-1, L-3, L-5, L-7, are never read by another pass in the
+//     same step), so a lane has 4 update chains + 2 residual chains in flight;
+//   * of the four neighbours of an update only two are read from shared memory: the point above this step's point is
+//     next step's horizontal neighbour inside the lane's own column pair, and this step's in-pair neighbour is next
+//     step's point below -- both stay in registers; the residual's own columns are pass 3's last three results;
+//   * a ring row holds its 64 columns in order with one double of padding after every 16: a lane's column (stride 16 B
+//     across the warp) then hits 16 different bank pairs per half-warp, so every access is conflict-free, and the
+//     cp.async copies read whole sectors of global memory;
+//   * the loop is unrolled over the 16 ring slots: every shared-memory address is register + immediate.
+// Updates are in place: a pass only writes its own colour and reads the other one, exactly like the sequential
+// red-black passes, so every update sees the operands the reference's pass would see and the result is bit-identical.
+// Halo points (columns and, at strip ends, rows) are recomputed with the same expression; what lies outside the
+// "light cone" of the outputs may hold garbage and is never stored.
+//
+// Non-finite values.  The reference guards every operand with isfinite (pressure.cpp:84-88).  This kernel does not:
+// a non-finite operand makes the update non-finite (sums and products with positive constants cannot lose an Inf/NaN),
+// so it surfaces in a stored value or a residual term.  Those are tested; a hit sets Scalars::rb_redo and the guarded
+// tile kernel (k_rbgs_fused, launched right behind this one, a no-op otherwise) redoes the whole smooth() from the
+// untouched input buffer (p is ping-ponged).  For finite data the guards are identities, so the fast path is exact.
+#pragma once
+#include <type_traits>
+
+#include "kernels_pressure.cuh"
+
+#define RS_R 16     // ring rows (power of two): rows t-9 .. t live at step t, 4 more in flight
+#define RS_D 4      // rows in flight
+#define RS_OUT 52   // output columns per warp
+#define RS_HX 6     // halo columns (5 needed; 6 keeps X0 odd = 16-byte aligned pairs in global memory)
+#define RS_HY 5     // halo rows
+#define RS_WARPS 2  // warps per block (independent of each other)
+#define RS_ROW 68   // doubles per ring row: 64 columns + 1 pad after every 16
+#define RS_WDOUBLES (2 + RS_R * RS_ROW + 2 + RS_R * RS_ROW) // per warp: pad, p ring, pad, rhs ring
+#define RS_SMEM (RS_WARPS * RS_WDOUBLES * 8)
+
+__device__ __forceinline__ void rs_cp8(double *smem, const double *gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void rs_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void rs_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int POW2>
+__global__ void __launch_bounds__(32 * RS_WARPS, 6)
+    k_rbgs_stream(Geom g, const double *__restrict__ pin, double *__restrict__ pout, const double *__restrict__ rhs,
+                  Scalars *sc, double *partials, double tol, int RY, int nstrips, int finish) { pdl_begin();
+    extern __shared__ double rs_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double *ringp = rs_raw + w * RS_WDOUBLES + 2;   // [slot][RS_ROW]
+    double *ringr = ringp + RS_R * RS_ROW + 2;      // [slot][RS_ROW]
+    const int wx = blockIdx.x * RS_WARPS + w;
+    const bool done = sc->done != 0; // converged earlier: only carry p over to the other buffer
+    double acc[1] = {0.0};
+    int redo = 0;
+    if (wx < nstrips) {
+        const int X0 = 1 + RS_OUT * wx - RS_HX; // odd: (X0 + CFD_XOFF) is even, pairs are 16-byte aligned
+        const int a = X0 + 2 * lane;            // this lane's columns: a, a + 1
+        // rows this launch stores: the slab's cell rows plus the ghost rows the slab owns (carried over unchanged)
+        const int ylo = g.bottom ? 0 : 1, yhi = g.top ? g.ny + 1 : g.ny;
+        const int y0 = ylo + blockIdx.y * RY, y1 = min(y0 + RY - 1, yhi);
+        // rows that may be updated: cells of this slab and, towards a neighbouring slab, its exchanged halo rows
+        const int jlo = g.bottom ? 1 : 1 - RS_HY + 1, jhi = g.top ? g.ny : g.ny + RS_HY - 1;
+        const bool c0 = a >= 1 && a <= g.nx, c1 = a + 1 >= 1 && a + 1 <= g.nx; // interior columns
+        // pairs this lane stores: the 26 output pairs, plus the pair holding ghost column 0 in the first strip
+        const bool st_lane = ((lane >= RS_HX / 2 && lane < RS_HX / 2 + RS_OUT / 2) || (wx == 0 && lane == RS_HX / 2 - 1)) && a <= g.nx + 1;
+        const bool in_lane = lane >= RS_HX / 2 && lane < RS_HX / 2 + RS_OUT / 2;
+        const size_t P = g.P;
+        if (done) {
+            if (st_lane)
+                for (int jj = y0; jj <= y1; ++jj) {
+                    const size_t o = gidx(g, a, jj);
+                    *reinterpret_cast<double2 *>(pout + o) = *reinterpret_cast<const double2 *>(pin + o);
+                }
+        } else {
+            const int ys = y0 - RS_HY;                 // first row loaded (relative row 0)
+            const int nload = y1 + RS_HY - ys + 1;     // rows loaded
+            const int T = y1 + 9 - ys + 1;             // steps: the residual (row L-9) must reach y1
+            // cp.async: lane l copies columns X0+l and X0+32+l of the next row (whole sectors per instruction)
+            const double *gp_next = pin + gidx(g, X0 + lane, ys);
+            const double *gr_next = rhs + gidx(g, X0 + lane, ys);
+            double *po = pout + gidx(g, a, ys - 7);    // where pass 3's row (relative t-7) is stored at step t
+            // colour (ii + jj + j0) & 1 of column a (odd) in relative row 0:
+            const int par0 = (ys + g.j0 + 1) & 1;
+            const double idx2 = g.idx2, idy2 = g.idy2;
+            // ring column i lives at i + (i >> 4)
+            const int cpA = lane + (lane >> 4), cpB = 32 + lane + 2 + (lane >> 4); // cp.async destinations
+            const int lb = 2 * lane + (lane >> 3);                                  // column a
+            // columns a - 1 and a + 2; lanes 0 / 31 have no such neighbour in the strip (their results are halo garbage
+            // anyway) and read a word of their own whose bank nobody else in the half-warp uses
+            const int lbL = lane == 0 ? 0 : 2 * lane - 1 + ((2 * lane - 1) >> 4);
+            const int lbR = lane == 31 ? 66 : 2 * lane + 2 + ((2 * lane + 2) >> 4);
+            // x = colour ^ row parity.  Column offset of the updated point in its pair: E[x] = x ^ par0.
+            const int E0 = par0, E1 = par0 ^ 1;
+            double *const Bo[2] = {ringp + lb + E0, ringp + lb + E1};               // the updated point
+            const double *const Bh[2] = {ringp + (E0 ? lbR : lbL), ringp + (E1 ? lbR : lbL)}; // its neighbour in the adjacent lane's pair
+            const double *const Ro[2] = {ringr + lb + E0, ringr + lb + E1};
+            const bool colok[2] = {E0 ? c1 : c0, E1 ? c1 : c0};
+            const int t_jlo = jlo - ys, t_jhi = jhi - ys;                  // updatable relative rows
+            const int t_st0 = y0 - ys, t_st1 = y1 - ys;                    // stored relative rows
+            const int rr_first = max(y0, 1) - ys, rr_last = min(y1, g.ny) - ys; // residual rows (relative)
+            const bool inA = in_lane && c0, inB = in_lane && c1;
+            auto issue = [&](int rt, int slot) { // request relative row rt into ring slot `slot`
+                if (rt < nload) {
+                    rs_cp8(ringp + slot * RS_ROW + cpA, gp_next);
+                    rs_cp8(ringp + slot * RS_ROW + cpB, gp_next + 32);
+                    rs_cp8(ringr + slot * RS_ROW + cpA, gr_next);
+                    rs_cp8(ringr + slot * RS_ROW + cpB, gr_next + 32);
+                }
+                rs_commit();
+                gp_next += P, gr_next += P;
+            };
+#pragma unroll
+            for (int d = 0; d < RS_D; ++d) issue(d, d);
+            double ho[4], bo[4];           // per pass: in-pair horizontal neighbour, neighbour below (see header)
+            double r1[2], r2[2], r3[2];    // the lane's final pairs of rows t-8, t-9, t-10 (pass 3's last three rows)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ho[k] = bo[k] = 0.0;
+            r1[0] = r1[1] = r2[0] = r2[1] = r3[0] = r3[1] = 0.0;
+            int xbits = 0; // max over the stored values and residual terms of their exponent bits: 0x7ff00000 = non-finite
+            // 16 steps = one turn of the ring.  FILL: the first turn, where the passes start one after the other.
+            // A turn always runs all 16 steps (steps past T only touch the ring), so the body is straight-line code.
+            auto turn = [&](const int tb, auto fill_c) {
+                constexpr bool FILL = decltype(fill_c)::value;
+#pragma unroll
+                for (int u = 0; u < RS_R; ++u) {
+                    const int t = tb + u; // tb is a multiple of 16: slot of relative row t-j is (u-j) & 15, its parity (u-j) & 1
+                    rs_wait<RS_D - 1>();
+                    __syncwarp();
+                    issue(t + RS_D, (u + RS_D) & (RS_R - 1));
+                    double cur[2] = {0.0, 0.0}; // the lane's pair of row t-7 after pass 3
+                    // ---- four colour passes (pressure.cpp:70-94), pass k in relative row t-1-2k
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int rt = t - 1 - 2 * k;
+                        if (FILL && rt < 1) continue; // warp-uniform
+                        const int q = k & 1;                          // colour this pass updates
+                        const int S = (u - 1 - 2 * k) & (RS_R - 1);   // slot of row rt
+                        const int x = q ^ ((u + 1) & 1);              // colour ^ parity of rt
+                        if (FILL && rt == 1) {                        // first row of this pass: nothing carried yet
+                            ho[k] = Bo[x ^ 1][S * RS_ROW];                         // the other column of the pair, this row
+                            bo[k] = Bo[x][((S - 1) & (RS_R - 1)) * RS_ROW];        // this column, the row below
+                        }
+                        const double pt = Bo[x][((S + 1) & (RS_R - 1)) * RS_ROW]; // this column, the row above
+                        const double ph = Bh[x][S * RS_ROW];          // the horizontal neighbour in the adjacent lane's pair
+                        const double rv = Ro[x][S * RS_ROW];
+                        const double sum = (ph + ho[k]) * idx2 + (pt + bo[k]) * idy2;
+                        double xv = POW2 ? (rv + sum) * g.inv_denom : (rv + sum) / g.denom;
+                        const bool ok = (!FILL || rt >= t_jlo) && rt <= t_jhi && colok[x];
+                        if (ok) Bo[x][S * RS_ROW] = xv;
+                        if (k == 3) {                                  // row rt is final: the lane's pair, column order
+                            if (!ok) xv = Bo[x][S * RS_ROW];
+                            const bool e = x ? E1 : E0;
+                            cur[0] = e ? ho[k] : xv;
+                            cur[1] = e ? xv : ho[k];
+                            if (rt >= t_st0 && rt <= t_st1 && st_lane) {
+                                xbits = max(xbits, max(__double2hiint(cur[0]) & 0x7ff00000, __double2hiint(cur[1]) & 0x7ff00000));
+                                *reinterpret_cast<double2 *>(po) = make_double2(cur[0], cur[1]);
+                            }
+                        }
+                        bo[k] = ho[k];
+                        ho[k] = pt;
+                    }
+                    po += P;
+                    // ---- residual (pressure.cpp:96-110) in relative row rr = t-9: r = rhs - L p, sum of r^2.  Rows
+                    //      rr-1, rr, rr+1 of the lane's own columns are pass 3's last three results (registers).
+                    const int rr = t - 9;
+                    if ((!FILL || rr >= rr_first) && rr <= rr_last) {
+                        const int SR = (u - 9) & (RS_R - 1);
+                        const double hl = ringp[SR * RS_ROW + lbL];    // column a - 1
+                        const double hr = ringp[SR * RS_ROW + lbR];    // column a + 2
+                        const double rhA = ringr[SR * RS_ROW + lb], rhB = ringr[SR * RS_ROW + lb + 1];
+                        const double ApA = (r2[1] - 2.0 * r2[0] + hl) * idx2 + (r1[0] - 2.0 * r2[0] + r3[0]) * idy2;
+                        const double ApB = (hr - 2.0 * r2[1] + r2[0]) * idx2 + (r1[1] - 2.0 * r2[1] + r3[1]) * idy2;
+                        const double resA = rhA - ApA, resB = rhB - ApB;
+                        // (a finite term may square to Inf exactly as in the reference's dot(): test the term, not acc)
+                        xbits = max(xbits, max((inA ? __double2hiint(resA) : 0) & 0x7ff00000, (inB ? __double2hiint(resB) : 0) & 0x7ff00000));
+                        acc[0] += inA ? resA * resA : 0.0;
+                        acc[0] += inB ? resB * resB : 0.0;
+                    }
+                    r3[0] = r2[0], r3[1] = r2[1];
+                    r2[0] = r1[0], r2[1] = r1[1];
+                    r1[0] = cur[0], r1[1] = cur[1];
+                }
+            };
+            turn(0, std::true_type{});
+            for (int tb = RS_R; tb < T; tb += RS_R) turn(tb, std::false_type{});
+            if (xbits == 0x7ff00000) redo = 1;
+            rs_wait<0>();
+        }
+    }
+    if (done) return;
+    if (redo) *reinterpret_cast<volatile int *>(&sc->rb_redo) = 1;
+    grid_sum<1>(acc, partials, &sc->ticket[2], [=](double(&t)[1]) {
+        if (*reinterpret_cast<volatile int *>(&sc->rb_redo)) return; // the guarded kernel behind us redoes this smooth()
+        if (finish) rbgs_tail(sc, t[0], tol);                        // vcycle loop exit, pressure.cpp:120
+        else sc->red[0] = t[0];
+    });
+}

@@ -161,11 +161,14 @@ def test_stage_kernels_bit_exact(cfd, port, nx, ny, Lx, Ly, variant):
     assert same_or_nan(gdu, du) and same_or_nan(gdv, dv)
 
 
-@pytest.mark.parametrize("nx,ny,Lx,Ly", [(16, 16, 1.0, 1.0), (37, 21, 2.0, 0.9), (64, 32, 2.0, 1.0), (130, 67, 1.0, 1.0)])
-def test_pressure_solve_mg_bit_exact(cfd, port, nx, ny, Lx, Ly):
+@pytest.mark.parametrize("variant", [1, 2])  # 1: streaming smoother (+ guarded slow path), 2: tile smoother alone
+@pytest.mark.parametrize("nx,ny,Lx,Ly", [(16, 16, 1.0, 1.0), (37, 21, 2.0, 0.9), (64, 32, 2.0, 1.0), (130, 67, 1.0, 1.0),
+                                         (52, 300, 1.0, 1.0), (53, 40, 1.0, 1.0), (421, 533, 1.7, 0.9)])
+def test_pressure_solve_mg_bit_exact(cfd, port, nx, ny, Lx, Ly, variant):
     _, _, p = rand_fields(nx, ny, 5)
     rhs = rand_fields(nx, ny, 6)[2]
     s = cfd.Solver(nx, ny, Lx, Ly)
+    s.set_variant(variant)
     for vcycles, tol in ((1, 1e-9), (3, 1e-9), (3, 1e3)):
         s.upload(p=p, rhs=rhs)
         op = p.copy()
@@ -175,6 +178,38 @@ def test_pressure_solve_mg_bit_exact(cfd, port, nx, ny, Lx, Ly):
         assert same(gp, op), (vcycles, nbad(gp, op), where_bad(gp, op))
         assert git == oit
         assert abs(gres - ores) <= 1e-12 * ores
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_pressure_solve_mg_nonfinite_operands(cfd, port, variant):
+    """Non-finite p / rhs entries: the reference reads them as 0 (pressure.cpp:84-88).  The streaming smoother detects
+    them and hands the smooth() to the guarded tile kernel; the result must still be the reference's, bit for bit."""
+    nx, ny, Lx, Ly = 200, 150, 1.0, 1.0
+    _, _, p = rand_fields(nx, ny, 15)
+    rhs = rand_fields(nx, ny, 16)[2]
+    p[7, 9] = np.nan
+    p[100, 150] = np.inf
+    p[0, 30] = -np.inf      # a ghost cell
+    rhs[60, 61] = np.inf
+    rhs[149, 199] = np.nan
+    s = cfd.Solver(nx, ny, Lx, Ly)
+    s.set_variant(variant)
+    for vcycles in (1, 2):
+        s.upload(p=p, rhs=rhs)
+        op = p.copy()
+        ores, oit = port.pressure_solve(nx, ny, Lx, Ly, op, rhs, cfdo.make_params("mg", vcycles=vcycles, tol=1e-9))
+        gres, git = s.pressure_solve(cfd.make_params("mg", vcycles=vcycles, tol=1e-9))
+        gp = s.download()[2]
+        assert same_or_nan(gp, op), (vcycles, nbad(gp, op), where_bad(gp, op))
+        assert git == oit and abs(gres - ores) <= 1e-12 * ores
+    # and a clean solve afterwards takes the fast path again with the same answer
+    _, _, p2 = rand_fields(nx, ny, 17)
+    rhs2 = rand_fields(nx, ny, 18)[2]
+    s.upload(p=p2, rhs=rhs2)
+    op = p2.copy()
+    port.pressure_solve(nx, ny, Lx, Ly, op, rhs2, cfdo.make_params("mg", vcycles=2, tol=1e-9))
+    s.pressure_solve(cfd.make_params("mg", vcycles=2, tol=1e-9))
+    assert same(s.download()[2], op)
 
 
 @pytest.mark.parametrize("variant", [0, 1])
@@ -331,7 +366,7 @@ def test_kernel_variants_agree_bitwise_1024(cfd):
     nx = ny = 1024
     u, v, p = rand_fields(nx, ny, 42)
     outs = []
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         s = cfd.Solver(nx, ny, 1.0, 1.0)
         s.set_variant(variant)
         s.upload(u, v, p)
@@ -339,8 +374,9 @@ def test_kernel_variants_agree_bitwise_1024(cfd):
         for _ in range(2):
             s.step(bc, Re, CFL, cfd.make_params("mg"))
         outs.append(s.download() + s.download_work())
-    for a, b in zip(*outs):
-        assert same(a, b), (nbad(a, b), where_bad(a, b))
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert same(a, b), (nbad(a, b), where_bad(a, b))
 
 
 def test_async_steps_match_sync_steps(cfd):
