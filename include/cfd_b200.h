@@ -115,6 +115,12 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
  * NVLink (CUDA IPC: halo rows stored straight into the neighbour's arrays, reductions fused with their scalar tails).
  * 2 is chosen when every rank could map every peer; CFD_B200_P2P=0 in the environment forces 1. */
 int cfd_b200_comm_mode(const cfd_b200_solver *s);
+/* Tuning / test hook: rows > 0 forces the streaming smoother with `rows` rows per strip on any grid size (the default,
+ * 0, picks the strip height from the grid and uses the tile smoother on grids too small to fill the GPU). */
+int cfd_b200_set_smoother_strip(cfd_b200_solver *s, int rows);
+/* Which kernel ran the last smooth() of --solver=mg (reference mode): 1 = streaming smoother (large grids), 2 = tile
+ * smoother (small grids, and the guarded slow path of 1), 3 = one launch per colour pass (variant 0), 0 = none yet. */
+int cfd_b200_last_smoother(const cfd_b200_solver *s);
 /* First owned cell row and number of owned cell rows of this handle (0, ny for a single-GPU handle). */
 int cfd_b200_slab_rows(const cfd_b200_solver *s, int *row0, int *nrows);
 

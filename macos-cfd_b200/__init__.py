@@ -124,6 +124,8 @@ def load_library(build: bool = True):
     L.cfd_b200_comm_id.argtypes = [C.c_void_p]
     L.cfd_b200_slab_rows.argtypes = [S, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.cfd_b200_comm_mode.argtypes = [S]
+    L.cfd_b200_last_smoother.argtypes = [S]
+    L.cfd_b200_set_smoother_strip.argtypes = [S, C.c_int]
     L.cfd_b200_destroy.argtypes = [S]
     L.cfd_b200_destroy.restype = None
     L.cfd_b200_upload.argtypes = [S, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -206,6 +208,15 @@ class Solver:
     def comm_mode(self) -> str:
         """How the slabs talk: "single", "nccl" (send/recv + allreduce) or "p2p" (peer memory over NVLink, CUDA IPC)."""
         return ("single", "nccl", "p2p")[self.L.cfd_b200_comm_mode(self.h)]
+
+    def set_smoother_strip(self, rows: int):
+        """rows > 0: force the streaming smoother with that strip height (tests / tuning); 0: automatic."""
+        self._check(self.L.cfd_b200_set_smoother_strip(self.h, rows))
+
+    @property
+    def last_smoother(self) -> str:
+        """Kernel that ran the last smooth() of the reference-mode mg solver."""
+        return ("none", "k_rbgs_stream", "k_rbgs_fused", "k_rbgs_colour x4 + k_rbgs_residual")[self.L.cfd_b200_last_smoother(self.h)]
 
     def _check(self, rc):
         if rc != 0:

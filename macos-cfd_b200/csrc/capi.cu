@@ -69,6 +69,8 @@ struct cfd_b200_solver {
     cudaStream_t stream = nullptr;
     long long launches = 0;
     int variant = 1;
+    int rb_strip = 0;      // > 0: force the streaming smoother with this many rows per strip (tests, tuning)
+    int last_smoother = 0; // which kernel ran the last smooth(): 1 streaming, 2 tile, 3 per-colour passes
     int pdl = 3; // programmatic dependent launch between consecutive kernels (bit mask, see cfd_b200_create_slab; CFD_B200_PDL=0 turns it off)
     bool cfl_cached = false;   // umax/vmax of the current device State are already in d_sc (from the last step)
     cfd_b200_bc last_bc{};
@@ -505,9 +507,10 @@ void enqueue_smooth(cfd_b200_solver *s, double tol, int finish) {
         // tile kernel is the better one (1024^2: 21 us per smooth against 25).
         int RY = 257;
         while (RY > 65 && (long long)gx * cdiv(nrows, RY) < 6LL * s->sm_count) RY = (RY - 1) / 2 + 1;
-        if (ry_env > 0) RY = ry_env;
+        const int forced = s->rb_strip > 0 ? s->rb_strip : ry_env;
+        if (forced > 0) RY = forced;
         const dim3 grid(gx, cdiv(nrows, RY));
-        if (ry_env <= 0 && (long long)grid.x * grid.y < 3LL * s->sm_count) stream = false;
+        if (forced <= 0 && (long long)grid.x * grid.y < 3LL * s->sm_count) stream = false;
         else if (g.denom_pow2)
             launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<1>, grid, dim3(32 * RS_WARPS), RS_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, RY, nstrips, finish);
         else
@@ -515,6 +518,7 @@ void enqueue_smooth(cfd_b200_solver *s, double tol, int finish) {
     }
     if (g.denom_pow2) launch_fused<1>(s, tol, ntx, nty, finish, stream);
     else launch_fused<0>(s, tol, ntx, nty, finish, stream);
+    s->last_smoother = stream ? 1 : 2;
 }
 
 // ---- EXTENSION: true geometric V-cycle (kernels_vcycle.cuh; algorithm = the CPU restatement cfd_vcycle.c of the test tree; parity unpinned) ----
@@ -711,6 +715,7 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp, bool in_step = 
         }
         dim3 cblock(32, 8), cgrid(cdiv(cdiv(g.nx, 2), 32), cdiv(g.ny, 8));
         dim3 rgrid(cdiv(g.nx, 256), g.ny < 256 ? g.ny : 256);
+        s->last_smoother = 3;
         for (int vc = 0; vc < pp->vcycles; ++vc) {
             for (int sweep = 0; sweep < 2; ++sweep) // the literal 2 of pressure.cpp:119
                 for (int colour = 0; colour < 2; ++colour) {
@@ -1074,6 +1079,14 @@ int cfd_b200_sync(cfd_b200_solver *s, cfd_b200_step_info *info) {
     if (s->h_sc->comm_error) return fail(CFD_B200_ECOMM, "rank %d: a peer did not arrive within %d s (peer-memory exchange)", s->rank, (int)(P2P_TIMEOUT_NS / 1000000000ull));
     return 0;
 }
+
+int cfd_b200_set_smoother_strip(cfd_b200_solver *s, int rows) {
+    if (!s || rows < 0) return fail(CFD_B200_EINVAL, "bad argument");
+    s->rb_strip = rows;
+    return 0;
+}
+
+int cfd_b200_last_smoother(const cfd_b200_solver *s) { return s ? s->last_smoother : 0; }
 
 int cfd_b200_comm_mode(const cfd_b200_solver *s) { return !s || s->nranks == 1 ? 0 : (s->p2p_on ? 2 : 1); }
 

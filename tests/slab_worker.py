@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--vcycles", type=int, default=2)
     ap.add_argument("--variant", type=int, default=1)
+    ap.add_argument("--strip", type=int, default=0)  # > 0: force the streaming smoother with this strip height
     ap.add_argument("--p2p", type=int, default=1)  # 0: force the NCCL path (CFD_B200_P2P=0)
     ap.add_argument("--out", required=True)
     a = ap.parse_args()
@@ -45,6 +46,7 @@ def main():
     s = cfd.Solver(a.nx, a.ny, a.Lx, a.Ly, device=local % torch.cuda.device_count(), rank=rank, nranks=world,
                    comm_id=ids[0])
     s.set_variant(a.variant)
+    s.set_smoother_strip(a.strip)
     bc, Re, CFL = cfd.preset(a.preset, a.Ly)
     pp = cfd.make_params(a.solver, vcycles=a.vcycles, tol=a.tol, pcg_max_iters=a.iters)
     r0, n = s.row0, s.nrows

@@ -50,18 +50,20 @@ def same(a, b):
     return np.array_equal(a.view(np.uint64), b.view(np.uint64))
 
 
-CASES = [(preset, solver, variant, 1) for solver, variant in (("mg", 1), ("mg", 0), ("pcg", 1))
-         for preset in ("jet", "lid", "shear")] + [("jet", "mg", 1, 0), ("shear", "pcg", 1, 0), ("lid", "mg", 0, 0)]
+# (preset, solver, variant, p2p, strip): strip > 0 forces the streaming smoother (automatic only on grids that fill the GPU)
+CASES = [(preset, solver, variant, 1, 0) for solver, variant in (("mg", 1), ("mg", 0), ("pcg", 1))
+         for preset in ("jet", "lid", "shear")] + [("jet", "mg", 1, 0, 0), ("shear", "pcg", 1, 0, 0), ("lid", "mg", 0, 0, 0)] + [
+         ("jet", "mg", 1, 1, 33), ("lid", "mg", 1, 1, 17), ("shear", "mg", 1, 0, 33)]
 
 
-@pytest.mark.parametrize("preset,solver,variant,p2p", CASES)
-def test_slabs_match_single_gpu(tmp_path, preset, solver, variant, p2p):
+@pytest.mark.parametrize("preset,solver,variant,p2p,strip", CASES)
+def test_slabs_match_single_gpu(tmp_path, preset, solver, variant, p2p, strip):
     """p2p=1: halo rows and reductions through peer memory (CUDA IPC over NVLink); p2p=0: the NCCL path."""
     n = min(ngpu(), 4)
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     kw = dict(preset=preset, solver=solver, nx=260, ny=203, steps=4, iters=60)
-    got = run_slabs(n, tmp_path, variant=variant, p2p=p2p, **kw)
+    got = run_slabs(n, tmp_path, variant=variant, p2p=p2p, strip=strip, **kw)
     assert str(got["comm_mode"]) == ("p2p" if p2p else "nccl")  # no silent fallback
     hist, (u, v, p, rhs), div_l2, vmax = run_single(kw)
     assert np.array_equal(got["hist"][:, 0], hist[:, 0])  # dt

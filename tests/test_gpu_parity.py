@@ -161,14 +161,16 @@ def test_stage_kernels_bit_exact(cfd, port, nx, ny, Lx, Ly, variant):
     assert same_or_nan(gdu, du) and same_or_nan(gdv, dv)
 
 
-@pytest.mark.parametrize("variant", [1, 2])  # 1: streaming smoother (+ guarded slow path), 2: tile smoother alone
+# strip > 0: the streaming smoother with that many rows per strip (it is automatic only on grids that fill the GPU);
+# strip = 0 on these sizes: the tile smoother
+@pytest.mark.parametrize("strip", [0, 17, 33, 257])
 @pytest.mark.parametrize("nx,ny,Lx,Ly", [(16, 16, 1.0, 1.0), (37, 21, 2.0, 0.9), (64, 32, 2.0, 1.0), (130, 67, 1.0, 1.0),
                                          (52, 300, 1.0, 1.0), (53, 40, 1.0, 1.0), (421, 533, 1.7, 0.9)])
-def test_pressure_solve_mg_bit_exact(cfd, port, nx, ny, Lx, Ly, variant):
+def test_pressure_solve_mg_bit_exact(cfd, port, nx, ny, Lx, Ly, strip):
     _, _, p = rand_fields(nx, ny, 5)
     rhs = rand_fields(nx, ny, 6)[2]
     s = cfd.Solver(nx, ny, Lx, Ly)
-    s.set_variant(variant)
+    s.set_smoother_strip(strip)
     for vcycles, tol in ((1, 1e-9), (3, 1e-9), (3, 1e3)):
         s.upload(p=p, rhs=rhs)
         op = p.copy()
@@ -178,10 +180,11 @@ def test_pressure_solve_mg_bit_exact(cfd, port, nx, ny, Lx, Ly, variant):
         assert same(gp, op), (vcycles, nbad(gp, op), where_bad(gp, op))
         assert git == oit
         assert abs(gres - ores) <= 1e-12 * ores
+        assert s.last_smoother == ("k_rbgs_stream" if strip else "k_rbgs_fused")
 
 
-@pytest.mark.parametrize("variant", [1, 2])
-def test_pressure_solve_mg_nonfinite_operands(cfd, port, variant):
+@pytest.mark.parametrize("strip", [0, 33])
+def test_pressure_solve_mg_nonfinite_operands(cfd, port, strip):
     """Non-finite p / rhs entries: the reference reads them as 0 (pressure.cpp:84-88).  The streaming smoother detects
     them and hands the smooth() to the guarded tile kernel; the result must still be the reference's, bit for bit."""
     nx, ny, Lx, Ly = 200, 150, 1.0, 1.0
@@ -193,7 +196,7 @@ def test_pressure_solve_mg_nonfinite_operands(cfd, port, variant):
     rhs[60, 61] = np.inf
     rhs[149, 199] = np.nan
     s = cfd.Solver(nx, ny, Lx, Ly)
-    s.set_variant(variant)
+    s.set_smoother_strip(strip)
     for vcycles in (1, 2):
         s.upload(p=p, rhs=rhs)
         op = p.copy()
@@ -259,10 +262,11 @@ def run_oracle(lib, preset, solver, nx, ny, Lx, Ly, steps, tol, iters, vcycles, 
     return hist, out
 
 
-def run_gpu(cfd, preset, solver, nx, ny, Lx, Ly, steps, tol, iters, vcycles, dt_override=0.0):
+def run_gpu(cfd, preset, solver, nx, ny, Lx, Ly, steps, tol, iters, vcycles, dt_override=0.0, strip=0):
     bc, Re, CFL = cfd.preset(preset, Ly)
     pp = cfd.make_params(solver, vcycles=vcycles, tol=tol, pcg_max_iters=iters)
     s = cfd.Solver(nx, ny, Lx, Ly)
+    s.set_smoother_strip(strip)
     if preset == "shear":
         s.upload(u=cfd.shear_initial_u(nx, ny, Ly))
     hist = []
@@ -299,6 +303,15 @@ def test_whole_runs_vs_oracle(cfd, port, preset, solver, grid):
     nx, ny, Lx, Ly = grid
     args = (preset, solver, nx, ny, Lx, Ly, 6, 1e-8, 200, 2)
     compare_run(solver, run_gpu(cfd, *args), run_oracle(port, *args), (preset, solver, grid))
+
+
+@pytest.mark.parametrize("preset", ["jet", "lid", "shear"])
+@pytest.mark.parametrize("grid,strip", [((64, 32, 2.0, 1.0), 17), ((130, 67, 1.0, 1.0), 33), ((300, 140, 2.0, 1.0), 65)])
+def test_whole_runs_mg_streaming_smoother_vs_oracle(cfd, port, preset, grid, strip):
+    """The streaming smoother (automatic only on grids that fill the GPU) forced onto oracle-sized grids: bit-exact."""
+    nx, ny, Lx, Ly = grid
+    args = (preset, "mg", nx, ny, Lx, Ly, 6, 1e-8, 200, 2)
+    compare_run("mg", run_gpu(cfd, *args, strip=strip), run_oracle(port, *args), (preset, grid, strip))
 
 
 @pytest.mark.parametrize("key", [f"{p}_{s}_{g}" for p in ("jet", "lid", "shear") for s in ("pcg", "mg")
@@ -408,14 +421,16 @@ def test_jet_mg_1024_vs_oracle(cfd):
     lib = cfdo.load("ref") if cfdo.have_ref() else cfdo.load("port")
     args = ("jet", "mg", 1024, 1024, 1.0, 1.0, 4, 1e-6, 200, 2)
     old = os.environ.get("OMP_NUM_THREADS")
-    compare_run("mg", run_gpu(cfd, *args), run_oracle(lib, *args), "cfg1")
+    o = run_oracle(lib, *args)
+    compare_run("mg", run_gpu(cfd, *args), o, "cfg1")
+    compare_run("mg", run_gpu(cfd, *args, strip=257), o, "cfg1, streaming smoother, 257-row strips")
 
 
 def test_full_size_properties_8192(cfd):
     """At BASELINE's full size (8192^2) the oracle is too slow for a field comparison; check properties that do not
     depend on size: (1) the BC pass is idempotent for non-periodic presets, (2) a projection step leaves s.rhs equal
     to the divergence of the final (u, v) and divergence_l2 agrees with info.div_after, (3) two identical runs are
-    bit-identical, (4) the top lid row carries the imposed value."""
+    bit-identical, (4) the top lid row carries the imposed value, (5) the streaming and the tile smoother agree bitwise."""
     nx = ny = 8192
     bc, Re, CFL = cfd.preset("lid", 1.0)
     pp = cfd.make_params("mg", vcycles=2)
@@ -430,12 +445,19 @@ def test_full_size_properties_8192(cfd):
     u2 = np.empty_like(u)
     s.download(u=u2)
     assert same(u, u2)
+    assert s.last_smoother == "k_rbgs_stream"
+    p1 = np.empty((ny + 2, nx + 2))
+    s.download(p=p1)
+    s.close()
+    # (3) + (5): a second run with the tile smoother (variant 2) instead of the streaming one gives the same bits
     t = cfd.Solver(nx, ny, 1.0, 1.0)
+    t.set_variant(2)
     for _ in range(2):
         t.step(bc, Re, CFL, pp)
-    u3 = np.empty_like(u)
-    t.download(u=u3)
-    assert same(u, u3)
+    assert t.last_smoother == "k_rbgs_fused"
+    u3, p3 = np.empty_like(u), np.empty_like(p1)
+    t.download(u=u3, p=p3)
+    assert same(u, u3) and same(p1, p3)
 
 
 def test_largest_single_gpu_grid_16384(cfd):
