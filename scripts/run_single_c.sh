@@ -1,18 +1,9 @@
 cd /root/repo; mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "mg or variants or whole_runs or golden or nonfinite or full_size or async" > gpurun_out/pytest_gpu.log 2>&1; tail -15 gpurun_out/pytest_gpu.log
-for v in 1 2; do
- for wl in jet_mg_8192 jet_mg_1024; do
-  timeout 300 python bench.py --steps 16 --warmup 3 --no-e2e --no-cpu-baseline --workload $wl --variant $v > gpurun_out/rs_v${v}_$wl.json 2> gpurun_out/rs_v${v}_$wl.err
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "mg or variants or whole_runs or golden or nonfinite or full_size or async" > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+for wl in jet_mg_8192 lid_mg_8192; do
+  timeout 300 python bench.py --steps 16 --warmup 3 --no-e2e --no-cpu-baseline --workload $wl > gpurun_out/rs_$wl.json 2> gpurun_out/rs_$wl.err
   python - <<PY
 import json
-d=json.loads(open('gpurun_out/rs_v${v}_$wl.json').read().strip().splitlines()[-1]); print('variant',$v,'$wl', round(d['ms_per_step'],4), '%.3e'%d['value'], d['gpu_launches'], d['last_step'], d['roofline']['stages']['pressure_solve'])
-PY
- done
-done
-for ry in 129; do
-  CFD_B200_RB_RY=$ry timeout 300 python bench.py --steps 16 --warmup 3 --no-e2e --no-cpu-baseline --workload jet_mg_8192 > gpurun_out/rs_ry${ry}.json 2> gpurun_out/rs_ry${ry}.err
-  python - <<PY
-import json
-d=json.loads(open('gpurun_out/rs_ry${ry}.json').read().strip().splitlines()[-1]); print('RY',$ry, round(d['ms_per_step'],4), d['roofline']['stages']['pressure_solve'])
+d=json.loads(open('gpurun_out/rs_$wl.json').read().strip().splitlines()[-1]); print('$wl', round(d['ms_per_step'],4), '%.3e'%d['value'], d['gpu_launches'], d['roofline']['stages']['pressure_solve'], d['config']['probe_ms_per_step_from_reset'])
 PY
 done
