@@ -177,6 +177,32 @@ int cfd_b200_pressure_solve(cfd_b200_solver *s, const cfd_b200_params *pp, doubl
 int cfd_b200_subtract_grad_p(cfd_b200_solver *s, double dt);
 
 /* ---- measurement ---- */
+/* ---- Readers / mutators around the step, single-GPU handles -------------------------------
+ * An interactive caller can colour a frame and apply obstacles without the State ever crossing PCIe. */
+/* ScalarField, viz.hpp:8 -- same order */
+enum { CFD_B200_FIELD_U = 0, CFD_B200_FIELD_V, CFD_B200_FIELD_SPEED, CFD_B200_FIELD_PRESSURE, CFD_B200_FIELD_VORTICITY,
+       CFD_B200_FIELD_STREAMLINES, CFD_B200_FIELD_TEMPERATURE };
+typedef struct cfd_b200_field_stats {
+    double vmin, vmax;   /* compute_scalar's out-parameters, span rule included (viz.cpp:63-64) */
+    double mean, stddev; /* Gui::field_mean / field_std (gui.cpp:1452-1474) */
+} cfd_b200_field_stats;
+/* compute_scalar (viz.hpp:11-12, viz.cpp:6-65) on the device State: out (may be NULL) receives nx*ny doubles, index
+ * i + j*nx; st (may be NULL) the statistics of Gui::update_field_statistics (gui.cpp:1433-1481). */
+int cfd_b200_compute_scalar(cfd_b200_solver *s, int field, double *out, cfd_b200_field_stats *st);
+/* update_field_texture (gui.hpp / gui.cpp:1505-1561) without the GL upload: rgb receives nx*ny*3 bytes.  colormap =
+ * Gui::Colormap (gui.hpp:32-34; ids above 5 render as viridis, colormaps.cpp:124). */
+int cfd_b200_render_rgb(cfd_b200_solver *s, int field, int colormap, float scale_min, float scale_max, int normalize,
+                        float gamma, unsigned char *rgb);
+/* Shape, gui.hpp:14-23 (pos / size in cell units) */
+typedef struct cfd_b200_shape {
+    int type;    /* 0 = rectangle, 1 = circle */
+    float pos_x, pos_y, size_x, size_y;
+    int bc_type; /* 0 = solid wall, 1 = porous */
+    int enabled;
+} cfd_b200_shape;
+/* apply_shape_boundary_conditions (shapes.hpp:13, shapes.cpp:7-74) on the device u, v; asynchronous. */
+int cfd_b200_apply_shapes(cfd_b200_solver *s, const cfd_b200_shape *shapes, int n);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches claim). */
 long long cfd_b200_launch_count(const cfd_b200_solver *s);
 /* CUDA-event time of the stages of the most recent synchronous step, in ms.  Fills up to `n` entries of

@@ -46,6 +46,19 @@ class Params(C.Structure):
                 ("tol", C.c_double), ("pcg_max_iters", C.c_int), ("mg_mode", C.c_int)]
 
 
+class Shape(C.Structure):
+    """cfd_b200_shape = Shape of gui.hpp:14-23 (pos / size in cell units)."""
+    _fields_ = [("type", C.c_int), ("pos_x", C.c_float), ("pos_y", C.c_float), ("size_x", C.c_float),
+                ("size_y", C.c_float), ("bc_type", C.c_int), ("enabled", C.c_int)]
+
+
+class FieldStats(C.Structure):
+    _fields_ = [("vmin", C.c_double), ("vmax", C.c_double), ("mean", C.c_double), ("stddev", C.c_double)]
+
+
+FIELDS = {"u": 0, "v": 1, "speed": 2, "pressure": 3, "vorticity": 4, "streamlines": 5, "temperature": 6}  # viz.hpp:8
+
+
 class StepInfo(C.Structure):
     _fields_ = [("dt", C.c_double), ("residual", C.c_double), ("iters", C.c_int), ("pcg_breakdown", C.c_int),
                 ("div_before", C.c_double), ("div_after", C.c_double), ("nonfinite", C.c_int)]
@@ -125,6 +138,9 @@ def load_library(build: bool = True):
     L.cfd_b200_slab_rows.argtypes = [S, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.cfd_b200_comm_mode.argtypes = [S]
     L.cfd_b200_last_smoother.argtypes = [S]
+    L.cfd_b200_compute_scalar.argtypes = [S, C.c_int, C.c_void_p, C.POINTER(FieldStats)]
+    L.cfd_b200_render_rgb.argtypes = [S, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p]
+    L.cfd_b200_apply_shapes.argtypes = [S, C.POINTER(Shape), C.c_int]
     L.cfd_b200_set_smoother_strip.argtypes = [S, C.c_int]
     L.cfd_b200_destroy.argtypes = [S]
     L.cfd_b200_destroy.restype = None
@@ -277,6 +293,24 @@ class Solver:
         out = C.c_double()
         self._check(self.L.cfd_b200_max_velocity(self.h, C.byref(out)))
         return out.value
+
+    # readers / mutators around the step (viz.cpp, gui.cpp, shapes.cpp)
+    def compute_scalar(self, field: int, want_field=True):
+        """(out[ny, nx] or None, vmin, vmax, mean, std) of the visualisation scalar, computed on the device."""
+        out = np.empty((self.nrows, self.nx)) if want_field else None
+        st = FieldStats()
+        self._check(self.L.cfd_b200_compute_scalar(self.h, field, _addr(out), C.byref(st)))
+        return out, st.vmin, st.vmax, st.mean, st.stddev
+
+    def render_rgb(self, field: int, colormap: int, scale_min=0.0, scale_max=1.0, normalize=False, gamma=1.0):
+        rgb = np.empty((self.nrows, self.nx, 3), dtype=np.uint8)
+        self._check(self.L.cfd_b200_render_rgb(self.h, field, colormap, scale_min, scale_max, int(normalize), gamma,
+                                               rgb.ctypes.data))
+        return rgb
+
+    def apply_shapes(self, shapes):
+        arr = (Shape * max(len(shapes), 1))(*shapes)
+        self._check(self.L.cfd_b200_apply_shapes(self.h, arr, len(shapes)))
 
     # stage-level
     def apply_bc(self, bc, which=7):

@@ -3,6 +3,8 @@
 // here: every function forwards to libcfd_b200.so.  Errors from the device layer become std::runtime_error, except
 // allocation failures, which stay std::bad_alloc like the reference's (field.hpp:46,52).
 #include "b200_backend.hpp"
+#include "shapes.hpp"
+#include "viz.hpp"
 
 #include <cmath>
 #include <cstdio>
@@ -246,6 +248,59 @@ static double diagnostic(const Grid &g, const Field2D<double> &u, const Field2D<
 }
 double divergence_l2(const Grid &g, const Field2D<double> &u, const Field2D<double> &v) { return diagnostic(g, u, v, false); }
 double max_velocity(const Grid &g, const Field2D<double> &u, const Field2D<double> &v) { return diagnostic(g, u, v, true); }
+
+// ------------------------------------------------------------------------------------------------ viz / shapes
+// The device State to read: the stepping session's own when it mirrors `s` (no transfer in lazy mode when the device is
+// ahead), else a session fed with the caller's arrays.
+namespace {
+struct StateOnDevice {
+    b200::Scratch sc;
+    b200::Session *own;
+    StateOnDevice(const Grid &g, const State &s) : sc(g), own(b200::find_by_state(s.u.data, s.v.data)) {
+        if (own && own == sc.s && own->host_stale) return; // the device copy is the current one
+        check(cfd_b200_upload(sc.h(), s.u.data, s.v.data, s.p.data), "cfd_b200_upload");
+        if (own == sc.s) own->host_dirty = false;          // same arrays, now in sync
+        else sc.s->host_dirty = true, sc.s->host_stale = false;
+    }
+    cfd_b200_solver *h() const { return sc.h(); }
+};
+} // namespace
+
+void compute_scalar(const Grid &g, const State &s, ScalarField field, std::vector<double> &out, double &vmin, double &vmax) {
+    StateOnDevice d(g, s);
+    out.resize(static_cast<size_t>(g.nx) * g.ny);
+    cfd_b200_field_stats st{};
+    check(cfd_b200_compute_scalar(d.h(), static_cast<int>(field), out.data(), &st), "cfd_b200_compute_scalar");
+    vmin = st.vmin;
+    vmax = st.vmax;
+}
+b200::FieldStats b200::field_statistics(const Grid &g, const State &s, ScalarField field) {
+    StateOnDevice d(g, s);
+    cfd_b200_field_stats st{};
+    check(cfd_b200_compute_scalar(d.h(), static_cast<int>(field), nullptr, &st), "cfd_b200_compute_scalar");
+    return {st.vmin, st.vmax, st.mean, st.stddev};
+}
+void b200::render_rgb(const Grid &g, const State &s, ScalarField field, int colormap, float scale_min, float scale_max,
+                      bool normalize, float gamma, std::vector<unsigned char> &rgb) {
+    StateOnDevice d(g, s);
+    rgb.resize(static_cast<size_t>(g.nx) * g.ny * 3);
+    check(cfd_b200_render_rgb(d.h(), static_cast<int>(field), colormap, scale_min, scale_max, normalize ? 1 : 0, gamma,
+                              rgb.data()), "cfd_b200_render_rgb");
+}
+void apply_shape_boundary_conditions(const Grid &grid, State &state, const std::vector<Shape> &shapes) {
+    StateOnDevice d(grid, state);
+    std::vector<cfd_b200_shape> list;
+    for (const Shape &sh : shapes)
+        list.push_back({sh.type, sh.pos.x, sh.pos.y, sh.size.x, sh.size.y, sh.bcType, sh.enabled ? 1 : 0});
+    check(cfd_b200_apply_shapes(d.h(), list.data(), static_cast<int>(list.size())), "cfd_b200_apply_shapes");
+    const bool lazy = b200::coherence() == b200::Coherence::Lazy;
+    if (lazy && d.own == d.sc.s) {
+        d.own->host_stale = true; // the masked State lives on the device; sync_to_host() fetches it
+    } else {
+        check(cfd_b200_download(d.h(), state.u.data, state.v.data, nullptr, nullptr), "cfd_b200_download");
+        if (d.own == d.sc.s) d.own->host_stale = false;
+    }
+}
 
 // The remaining public functions of the reference headers operate on caller arrays: upload, run the stage kernel,
 // download.  They exist for source compatibility and kernel-level tests, not for speed.

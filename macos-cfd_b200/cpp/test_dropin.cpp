@@ -7,7 +7,9 @@
 #include <string>
 
 #include "b200_backend.hpp"
+#include "shapes.hpp"
 #include "solver/time_integrator.hpp"
+#include "viz.hpp"
 
 static void dump(const std::string &path, const Field2D<double> &f) {
     std::ofstream out(path, std::ios::binary);
@@ -78,6 +80,23 @@ int main(int argc, char **argv) {
         log << solver2.solve(p2, rhs2, pcg) << ' ' << solver2.last_iterations() << "\n";
         dump(dir + "/f_u.bin", u2), dump(dir + "/f_v.bin", v2), dump(dir + "/f_p.bin", p2), dump(dir + "/f_du.bin", du),
             dump(dir + "/f_rhs.bin", rhs2);
+
+        // the GUI's per-frame readers / mutators (main.cpp:246, :255-264) with the reference's own signatures
+        std::vector<Shape> shapes(2);
+        shapes[0].type = 0, shapes[0].pos = {30.0f, 8.0f}, shapes[0].size = {9.0f, 5.0f}, shapes[0].bcType = 0;
+        shapes[1].type = 1, shapes[1].pos = {50.5f, 20.25f}, shapes[1].size = {11.0f, 11.0f}, shapes[1].bcType = 1;
+        apply_shape_boundary_conditions(grid, st, shapes);
+        dump(dir + "/s_u.bin", st.u), dump(dir + "/s_v.bin", st.v);
+        std::vector<double> speed;
+        double vmin = 0.0, vmax = 0.0;
+        compute_scalar(grid, st, ScalarField::Speed, speed, vmin, vmax);
+        std::ofstream(dir + "/speed.bin", std::ios::binary)
+            .write(reinterpret_cast<const char *>(speed.data()), static_cast<std::streamsize>(speed.size() * sizeof(double)));
+        b200::FieldStats fs = b200::field_statistics(grid, st, ScalarField::Vorticity);
+        log << vmin << ' ' << vmax << ' ' << fs.vmin << ' ' << fs.vmax << ' ' << fs.mean << ' ' << fs.stddev << "\n";
+        std::vector<unsigned char> rgb;
+        b200::render_rgb(grid, st, ScalarField::Speed, /*Turbo*/ 4, 0.0f, 1.0f, false, 1.0f, rgb);
+        std::ofstream(dir + "/rgb.bin", std::ios::binary).write(reinterpret_cast<const char *>(rgb.data()), static_cast<std::streamsize>(rgb.size()));
     } catch (const std::exception &e) {
         std::fprintf(stderr, "test_dropin: %s\n", e.what());
         return 1;

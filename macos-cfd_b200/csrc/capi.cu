@@ -23,6 +23,7 @@
 #include "kernels_pcg_march.cuh"
 #include "kernels_pcg_coop.cuh"
 #include "p2p.cuh"
+#include "kernels_viz.cuh"
 
 namespace {
 
@@ -62,6 +63,8 @@ struct cfd_b200_solver {
     double *u1 = nullptr, *v1 = nullptr;           // TimeIntegrator work arrays (time_integrator.hpp:18-19)
     double *r = nullptr, *sA = nullptr, *sB = nullptr; // PressureSolver work arrays (pressure.hpp:29); z, Ap never stored
     double *scratch_u = nullptr, *scratch_v = nullptr; // stage-level entry points only (lazy)
+    double *viz_out = nullptr;                         // nx*ny visualisation scalar (lazy)
+    unsigned char *viz_rgb = nullptr;                  // nx*ny*3 bytes (lazy)
     Scalars *d_sc = nullptr;
     Scalars *h_sc = nullptr; // pinned
     double *partials = nullptr;
@@ -988,7 +991,8 @@ void cfd_b200_destroy(cfd_b200_solver *s) {
         if (s->mg[l].p) cudaFree(s->mg[l].p);
         if (s->mg[l].rhs) cudaFree(s->mg[l].rhs);
     }
-    double *fields[] = {s->arena, s->scratch_u, s->scratch_v, s->partials};
+    if (s->viz_rgb) cudaFree(s->viz_rgb);
+    double *fields[] = {s->arena, s->scratch_u, s->scratch_v, s->partials, s->viz_out};
     for (double *f : fields)
         if (f) cudaFree(f);
     if (s->d_sc) cudaFree(s->d_sc);
@@ -1234,6 +1238,92 @@ int cfd_b200_subtract_grad_p(cfd_b200_solver *s, double dt) {
     s->cfl_cached = false, s->halo_uv_valid = false;
     enqueue_project(s, nullptr, dt, 0);
     CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ---- readers / mutators around the step -------------------------------------------------
+namespace {
+// compute_scalar on the device; leaves the field in s->viz_out and {min, max, sum, sum^2} in h_sc->viz
+int viz_scalar_device(cfd_b200_solver *s, int field) {
+    if (s->nranks > 1) return fail(CFD_B200_EUNSUPPORTED, "the visualisation entry points are single-GPU");
+    if (field < 0 || field > VIZ_TEMPERATURE) return fail(CFD_B200_EINVAL, "bad scalar field %d", field);
+    const Geom &g = s->g;
+    if (!s->viz_out) CU(cudaMalloc(&s->viz_out, (size_t)g.nx * g.ny * sizeof(double)));
+    dim3 grid(cdiv(g.nx, 256), g.ny < 128 ? g.ny : 128);
+    LAUNCH(s, k_viz_scalar, grid, 256, g, s->u, s->v, s->p, field, s->viz_out, s->d_sc, s->partials);
+    CU(cudaMemcpyAsync(s->h_sc, s->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s->stream));
+    return 0;
+}
+} // namespace
+
+int cfd_b200_compute_scalar(cfd_b200_solver *s, int field, double *out, cfd_b200_field_stats *st) {
+    if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
+    CU(cudaSetDevice(s->device));
+    int rc = viz_scalar_device(s, field);
+    if (rc) return rc;
+    const size_t n = (size_t)s->g.nx * s->g.ny;
+    if (out) CU(cudaMemcpyAsync(out, s->viz_out, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    if (st) {
+        const double *z = s->h_sc->viz;
+        const double span = (1e-6 < z[1] - z[0]) ? z[1] - z[0] : 1e-6; // std::max(1e-6, vmax - vmin), viz.cpp:63
+        st->vmin = z[0];
+        st->vmax = z[0] + span;
+        // Gui::update_field_statistics, gui.cpp:1452-1474 (every value is finite after compute_scalar's own guard)
+        const double count = static_cast<double>(n);
+        st->mean = z[2] / count;
+        const double variance = (z[3] / count) - (st->mean * st->mean);
+        st->stddev = std::sqrt(0.0 < variance ? variance : 0.0);
+    }
+    return 0;
+}
+
+int cfd_b200_render_rgb(cfd_b200_solver *s, int field, int colormap, float scale_min, float scale_max, int normalize,
+                        float gamma, unsigned char *rgb) {
+    if (!s || !rgb) return fail(CFD_B200_EINVAL, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    int rc = viz_scalar_device(s, field);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(s->stream)); // vmin / vmax decide the scale (gui.cpp:1523-1532)
+    const size_t n = (size_t)s->g.nx * s->g.ny;
+    if (!s->viz_rgb) CU(cudaMalloc(&s->viz_rgb, 3 * n));
+    double vmin = s->h_sc->viz[0], hi = s->h_sc->viz[1];
+    double vmax = vmin + ((1e-6 < hi - vmin) ? hi - vmin : 1e-6);
+    if (scale_min != 0.0f || scale_max != 1.0f) {
+        vmin = scale_min;
+        vmax = scale_max;
+    }
+    const double scale = 1.0 / ((1e-6 < vmax - vmin) ? vmax - vmin : 1e-6);
+    const double inv_gamma = 1.0 / gamma; // "1.0 / gamma" with a float gamma, gui.cpp:1543
+    LAUNCH(s, k_viz_rgb, s->sm_count * 8, 256, n, s->viz_out, vmin, scale, normalize, inv_gamma, colormap, s->viz_rgb);
+    CU(cudaMemcpyAsync(rgb, s->viz_rgb, 3 * n, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int cfd_b200_apply_shapes(cfd_b200_solver *s, const cfd_b200_shape *shapes, int n) {
+    if (!s || (n > 0 && !shapes) || n < 0) return fail(CFD_B200_EINVAL, "bad argument");
+    if (s->nranks > 1) return fail(CFD_B200_EUNSUPPORTED, "the shape masks are single-GPU");
+    CU(cudaSetDevice(s->device));
+    const Geom &g = s->g;
+    auto clampi = [](int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); };
+    for (int k = 0; k < n; ++k) {
+        const cfd_b200_shape &sh = shapes[k];
+        if (!sh.enabled) continue;
+        // bounding box in cells, float -> int truncation, clamped to the grid (shapes.cpp:12-30); a circle's box ends at
+        // pos + size.x in both directions while its centre uses size.x/2 and size.y/2 (shapes.cpp:20-23, :42-44)
+        const float ex = sh.pos_x + sh.size_x, ey = sh.type == 0 ? sh.pos_y + sh.size_y : sh.pos_y + sh.size_x;
+        const int i0 = clampi(static_cast<int>(sh.pos_x), 0, g.nx - 1), j0 = clampi(static_cast<int>(sh.pos_y), 0, g.ny - 1);
+        const int i1 = clampi(static_cast<int>(ex), 0, g.nx - 1), j1 = clampi(static_cast<int>(ey), 0, g.ny - 1);
+        if (i1 < i0 || j1 < j0) continue;
+        const float cx = sh.pos_x + sh.size_x / 2.0f, cy = sh.pos_y + sh.size_y / 2.0f, rad = sh.size_x / 2.0f;
+        LAUNCH(s, k_shape_apply, dim3(cdiv(i1 - i0 + 1, 256), j1 - j0 + 1), 256, g, s->u, s->v, i0, j0, i1, j1,
+               sh.type != 0 ? 1 : 0, cx, cy, rad, sh.bc_type != 0 ? 1 : 0);
+    }
+    s->cfl_cached = false; // u, v changed behind the cached maxima
     CU(cudaGetLastError());
     return 0;
 }

@@ -72,6 +72,7 @@ struct Scalars {
     unsigned long long diag_max_bits;
     unsigned int ticket[4]; // last-block tickets of the grid reductions
     double red[4];          // row slabs: local partial sums handed to the allreduce, then to the k_*_fin kernels
+    double viz[4];          // k_viz_scalar: min, max, sum, sum of squares of the visualisation scalar
     int comm_error;         // a bounded peer wait (p2p.cuh) ran out: the step's results are invalid
     int rb_redo;            // k_rbgs_stream met a non-finite value: the guarded tile kernel redoes this smooth()
 };

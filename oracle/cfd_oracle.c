@@ -708,3 +708,161 @@ double cfdo_max_velocity(int nx, int ny, double Lx, double Ly, const double *u, 
     return max_speed(&g, u, v);
 }
 void cfdo_sanitize(double *a, long n) { sanitize(a, (size_t)n); }
+
+/* ================================================================== readers / mutators around the step
+ * (SURVEY.md §8f rank 4): the visualisation scalar (viz.cpp:6-65), its statistics (gui.cpp:1452-1474), the colour
+ * lookup (colormaps.cpp), the texture pixel loop (gui.cpp:1523-1551) and the obstacle masks (shapes.cpp:7-74). */
+
+/* one cell of compute_scalar, viz.cpp:20-55; (ii, jj) raw indices */
+static double viz_value(const grid_t *g, const double *u, const double *v, const double *p, int field, int ii, int jj) {
+    const int Pu = pitch_u(g), Pc = pitch_c(g);
+    double val = 0.0;
+    if (field == CFDO_FIELD_U || field == CFDO_FIELD_SPEED) {
+        double uc = 0.5 * (u[(size_t)jj * Pu + ii] + u[(size_t)jj * Pu + ii + 1]);
+        if (field == CFDO_FIELD_U) return isfinite(uc) ? uc : 0.0;
+        double vc = 0.5 * (v[(size_t)jj * Pc + ii] + v[(size_t)(jj + 1) * Pc + ii]);
+        val = sqrt(uc * uc + vc * vc);
+    } else if (field == CFDO_FIELD_V) {
+        val = 0.5 * (v[(size_t)jj * Pc + ii] + v[(size_t)(jj + 1) * Pc + ii]);
+    } else if (field == CFDO_FIELD_PRESSURE || field == CFDO_FIELD_TEMPERATURE) {
+        val = p[(size_t)jj * Pc + ii]; /* Temperature is a placeholder for pressure, viz.cpp:50-53 */
+    } else if (field == CFDO_FIELD_VORTICITY) {
+        double dv_dx = (v[(size_t)jj * Pc + ii + 1] - v[(size_t)jj * Pc + ii - 1]) / (2.0 * g->dx);
+        double du_dy = (u[(size_t)(jj + 1) * Pu + ii] - u[(size_t)(jj - 1) * Pu + ii]) / (2.0 * g->dy);
+        val = dv_dx - du_dy;
+    } /* Streamlines: placeholder 0.0, viz.cpp:45-49 */
+    return isfinite(val) ? val : 0.0;
+}
+
+void cfdo_compute_scalar(int nx, int ny, double Lx, double Ly, const double *u, const double *v, const double *p,
+                         int field, double *out, double *vmin, double *vmax) {
+    grid_t g = grid_make(nx, ny, Lx, Ly);
+    double lo = 1e30, hi = -1e30;
+    for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i) {
+            double val = viz_value(&g, u, v, p, field, i + 1, j + 1);
+            out[(size_t)j * nx + i] = val;
+            lo = min2(lo, val);
+            hi = max2(hi, val);
+        }
+    *vmin = lo;
+    *vmax = lo + max2(1e-6, hi - lo); /* viz.cpp:63-64 */
+}
+
+void cfdo_field_stats(const double *out, long n, double *mean, double *stddev) {
+    double sum = 0.0, sum_sq = 0.0;
+    long count = 0;
+    for (long k = 0; k < n; ++k)
+        if (isfinite(out[k])) {
+            sum += out[k];
+            sum_sq += out[k] * out[k];
+            ++count;
+        }
+    *mean = 0.0;
+    *stddev = 0.0;
+    if (count > 0) {
+        *mean = sum / (double)count;
+        *stddev = sqrt(max2(0.0, sum_sq / (double)count - *mean * *mean));
+    }
+}
+
+static int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+void cfdo_apply_shapes(int nx, int ny, double Lx, double Ly, double *u, double *v, const cfdo_shape *shapes, int n) {
+    grid_t g = grid_make(nx, ny, Lx, Ly);
+    const int Pu = pitch_u(&g), Pc = pitch_c(&g);
+    for (int k = 0; k < n; ++k) {
+        const cfdo_shape *sh = &shapes[k];
+        if (!sh->enabled) continue;
+        /* bounding box in cells (float -> int truncation), clamped to the grid: shapes.cpp:12-30 */
+        float ex = sh->type == 0 ? sh->pos_x + sh->size_x : sh->pos_x + sh->size_x; /* circle: pos + "radius" = size.x */
+        float ey = sh->type == 0 ? sh->pos_y + sh->size_y : sh->pos_y + sh->size_x;
+        int i0 = clampi((int)sh->pos_x, 0, nx - 1), j0 = clampi((int)sh->pos_y, 0, ny - 1);
+        int i1 = clampi((int)ex, 0, nx - 1), j1 = clampi((int)ey, 0, ny - 1);
+        float cx = sh->pos_x + sh->size_x / 2.0f, cy = sh->pos_y + sh->size_y / 2.0f, rad = sh->size_x / 2.0f;
+        for (int j = j0; j <= j1; ++j)
+            for (int i = i0; i <= i1; ++i) {
+                if (sh->type != 0) { /* circle: cell centre within the radius, all in float (shapes.cpp:41-47) */
+                    float dx = ((float)i + 0.5f) - cx, dy = ((float)j + 0.5f) - cy;
+                    if (!(dx * dx + dy * dy <= rad * rad)) continue;
+                }
+                double *pu = &u[(size_t)(j + 1) * Pu + i + 1], *pv = &v[(size_t)(j + 1) * Pc + i + 1];
+                if (sh->bc_type == 0) { /* solid: the cell's left and bottom face */
+                    *pu = 0.0;
+                    *pv = 0.0;
+                } else { /* porous: 90 % reduction */
+                    *pu *= 0.1;
+                    *pv *= 0.1;
+                }
+            }
+    }
+}
+
+/* colormaps.cpp: degree-6 Horner fits (viridis, plasma), piecewise ramps (jet, rdylbu), quartic in power form (turbo) */
+static const float CM_HORNER[2][7][3] = {
+    {{0.2777273272234177f, 0.005407344544966578f, 0.3340998053353061f},
+     {0.1050930431085774f, 1.404613529898575f, 1.384590162594685f},
+     {-0.3308618287255563f, 0.214847559468213f, 0.09509516302823659f},
+     {-4.634230498983486f, -5.799100973351585f, -19.33244095627987f},
+     {6.228269936347081f, 14.17993336680509f, 56.69055260068105f},
+     {4.776384997670288f, -13.74514537774601f, -65.35303263337234f},
+     {-5.435455855934631f, 12.86216349749025f, 26.312873249486f}},
+    {{0.05873234392399702f, 0.02333670892565664f, 0.5433401826748754f},
+     {2.176514634195958f, 0.2383834171260182f, 0.7539604599784036f},
+     {-2.689460476458034f, -7.455851135738909f, 3.110799939717086f},
+     {6.130348345893603f, 42.3461881477227f, -28.51885465332158f},
+     {-11.10743619062271f, -82.66631104428044f, 60.13984767418263f},
+     {10.02306557647065f, 71.41361770095349f, -54.07218655560067f},
+     {-3.658713842777788f, -22.93153465461149f, 18.19190778539828f}}};
+static const float CM_TURBO[5][3] = {{0.18995f, 0.07176f, 0.23217f}, {0.30315f, 0.50427f, 0.94791f},
+                                     {0.38343f, 0.87344f, 0.54467f}, {0.98853f, 0.64411f, 0.09395f},
+                                     {0.95839f, 0.82344f, 0.08425f}};
+static float clampf01(float x) { return (x < 0.0f) ? 0.0f : ((1.0f < x) ? 1.0f : x); }
+
+void cfdo_apply_colormap(int colormap, float t, unsigned char *rgb) {
+    float c[3];
+    if (colormap == 2) { /* jet, colormaps.cpp:45-71 */
+        if (t < 0.125f) { c[0] = 0.0f; c[1] = 0.0f; c[2] = 0.5f + 4.0f * t; }
+        else if (t < 0.375f) { c[0] = 0.0f; c[1] = 4.0f * (t - 0.125f); c[2] = 1.0f; }
+        else if (t < 0.625f) { c[0] = 4.0f * (t - 0.375f); c[1] = 1.0f; c[2] = 1.0f - 4.0f * (t - 0.375f); }
+        else if (t < 0.875f) { c[0] = 1.0f; c[1] = 1.0f - 4.0f * (t - 0.625f); c[2] = 0.0f; }
+        else { c[0] = 1.0f - 4.0f * (t - 0.875f); c[1] = 0.0f; c[2] = 0.0f; }
+    } else if (colormap == 3) { /* grayscale */
+        c[0] = c[1] = c[2] = t;
+    } else if (colormap == 4) { /* turbo, :77-96 */
+        float t2 = t * t, t3 = t2 * t, t4 = t3 * t;
+        for (int k = 0; k < 3; ++k)
+            c[k] = clampf01(CM_TURBO[0][k] + CM_TURBO[1][k] * t + CM_TURBO[2][k] * t2 + CM_TURBO[3][k] * t3 + CM_TURBO[4][k] * t4);
+    } else if (colormap == 5) { /* rdylbu, :98-112 */
+        if (t < 0.5f) { c[0] = 1.0f; c[1] = 2.0f * t; c[2] = 0.0f; }
+        else { float t2 = 2.0f * (t - 0.5f); c[0] = 1.0f - t2; c[1] = 1.0f - t2; c[2] = t2; }
+    } else { /* viridis (0 and every unknown id), plasma (1) */
+        const float(*q)[3] = CM_HORNER[colormap == 1 ? 1 : 0];
+        for (int k = 0; k < 3; ++k) {
+            float acc = q[6][k];
+            for (int d = 5; d >= 1; --d) acc = q[d][k] + t * acc;
+            c[k] = clampf01(q[0][k] + t * acc);
+        }
+    }
+    for (int k = 0; k < 3; ++k) rgb[k] = (unsigned char)(c[k] * 255.0f);
+}
+
+void cfdo_render_rgb(int nx, int ny, double Lx, double Ly, const double *u, const double *v, const double *p, int field,
+                     int colormap, float scale_min, float scale_max, int normalize, float gamma, unsigned char *rgb) {
+    size_t n = (size_t)nx * ny;
+    double *tmp = (double *)malloc(n * sizeof(double));
+    double vmin, vmax;
+    cfdo_compute_scalar(nx, ny, Lx, Ly, u, v, p, field, tmp, &vmin, &vmax);
+    if (scale_min != 0.0f || scale_max != 1.0f) {
+        vmin = scale_min;
+        vmax = scale_max;
+    }
+    double scale = 1.0 / max2(1e-6, vmax - vmin);
+    for (size_t k = 0; k < n; ++k) {
+        double val = normalize ? fabs(tmp[k]) : tmp[k];
+        double norm = clamp3((val - vmin) * scale, 0.0, 1.0);
+        norm = pow(norm, 1.0 / gamma);
+        cfdo_apply_colormap(colormap, (float)norm, rgb + 3 * k);
+    }
+    free(tmp);
+}

@@ -30,6 +30,16 @@ class BC(C.Structure):
                 ("jet_center", C.c_double), ("jet_width", C.c_double)]
 
 
+class Shape(C.Structure):
+    """gui.hpp:14-23 (pos / size in cell units)."""
+    _fields_ = [("type", C.c_int), ("pos_x", C.c_float), ("pos_y", C.c_float), ("size_x", C.c_float),
+                ("size_y", C.c_float), ("bc_type", C.c_int), ("enabled", C.c_int)]
+
+
+FIELDS = {"u": 0, "v": 1, "speed": 2, "pressure": 3, "vorticity": 4, "streamlines": 5, "temperature": 6}  # viz.hpp:8
+COLORMAPS = {"viridis": 0, "plasma": 1, "jet": 2, "grayscale": 3, "turbo": 4, "rdylbu": 5, "rdbu": 6, "coolwarm": 7}
+
+
 class Params(C.Structure):
     _fields_ = [("solver", C.c_int), ("mg_levels", C.c_int), ("vcycles", C.c_int), ("rbgs_sweeps", C.c_int),
                 ("tol", C.c_double), ("pcg_max_iters", C.c_int)]
@@ -130,6 +140,12 @@ class Lib:
         L.cfdo_divergence_l2.restype = L.cfdo_max_velocity.restype = C.c_double
         L.cfdo_divergence_l2.argtypes = L.cfdo_max_velocity.argtypes = g + [_dp, _dp]
         L.cfdo_sanitize.argtypes = [_dp, C.c_long]
+        L.cfdo_compute_scalar.argtypes = g + [_dp, _dp, _dp, C.c_int, _dp, _dp, _dp]
+        L.cfdo_field_stats.argtypes = [_dp, C.c_long, _dp, _dp]
+        L.cfdo_apply_shapes.argtypes = g + [_dp, _dp, C.POINTER(Shape), C.c_int]
+        L.cfdo_apply_colormap.argtypes = [C.c_int, C.c_float, C.POINTER(C.c_ubyte)]
+        L.cfdo_render_rgb.argtypes = g + [_dp, _dp, _dp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float,
+                                          C.POINTER(C.c_ubyte)]
 
     # ---- stage-level wrappers (arrays are modified in place) ----
     def apply_bc(self, which, nx, ny, Lx, Ly, a, bc):
@@ -169,6 +185,31 @@ class Lib:
 
     def sanitize(self, a):
         self.L.cfdo_sanitize(_ptr(a), a.size)
+
+    # ---- readers / mutators around the step (viz.cpp, shapes.cpp, colormaps.cpp, gui.cpp) ----
+    def compute_scalar(self, nx, ny, Lx, Ly, u, v, p, field):
+        """(out[ny, nx], vmin, vmax, mean, std): compute_scalar + the statistics of Gui::update_field_statistics."""
+        out = np.empty((ny, nx))
+        lo, hi, mean, std = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        self.L.cfdo_compute_scalar(nx, ny, Lx, Ly, _ptr(u), _ptr(v), _ptr(p), field, _ptr(out), C.byref(lo), C.byref(hi))
+        self.L.cfdo_field_stats(_ptr(out), out.size, C.byref(mean), C.byref(std))
+        return out, lo.value, hi.value, mean.value, std.value
+
+    def apply_shapes(self, nx, ny, Lx, Ly, u, v, shapes):
+        arr = (Shape * len(shapes))(*shapes)
+        self.L.cfdo_apply_shapes(nx, ny, Lx, Ly, _ptr(u), _ptr(v), arr, len(shapes))
+
+    def apply_colormap(self, colormap, t):
+        rgb = (C.c_ubyte * 3)()
+        self.L.cfdo_apply_colormap(colormap, t, rgb)
+        return tuple(rgb)
+
+    def render_rgb(self, nx, ny, Lx, Ly, u, v, p, field, colormap, scale_min=0.0, scale_max=1.0, normalize=False,
+                   gamma=1.0):
+        rgb = np.empty((ny, nx, 3), dtype=np.uint8)
+        self.L.cfdo_render_rgb(nx, ny, Lx, Ly, _ptr(u), _ptr(v), _ptr(p), field, colormap, scale_min, scale_max,
+                               int(normalize), gamma, rgb.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        return rgb
 
     def vcycle_solve(self, nx, ny, Lx, Ly, p, rhs, mg_levels=3, vcycles=2, rbgs_sweeps=2, tol=1e-6):
         """True geometric V-cycle (oracle/cfd_vcycle.c; port only -- the reference has no such code)."""

@@ -79,6 +79,30 @@ double cfdo_divergence_l2(int nx, int ny, double Lx, double Ly, const double *u,
 double cfdo_max_velocity(int nx, int ny, double Lx, double Ly, const double *u, const double *v);
 void cfdo_sanitize(double *a, long n);
 
+/* ---- host-side readers / mutators around the step ---------------------------------- */
+/* ScalarField order of viz.hpp:8 */
+enum { CFDO_FIELD_U = 0, CFDO_FIELD_V, CFDO_FIELD_SPEED, CFDO_FIELD_PRESSURE, CFDO_FIELD_VORTICITY,
+       CFDO_FIELD_STREAMLINES, CFDO_FIELD_TEMPERATURE };
+/* compute_scalar (viz.cpp:6-65): out = nx*ny doubles (index i + j*nx); vmin / vmax after the span rule. */
+void cfdo_compute_scalar(int nx, int ny, double Lx, double Ly, const double *u, const double *v, const double *p,
+                         int field, double *out, double *vmin, double *vmax);
+/* mean / standard deviation of Gui::update_field_statistics (gui.cpp:1433-1481) over `out` */
+void cfdo_field_stats(const double *out, long n, double *mean, double *stddev);
+/* Shape of gui.hpp:14-23 (pos / size in cell units, float) */
+typedef struct cfdo_shape {
+    int type;     /* 0 = rectangle, 1 = circle */
+    float pos_x, pos_y, size_x, size_y;
+    int bc_type;  /* 0 = solid wall, 1 = porous */
+    int enabled;
+} cfdo_shape;
+/* apply_shape_boundary_conditions (shapes.cpp:7-74) on u, v */
+void cfdo_apply_shapes(int nx, int ny, double Lx, double Ly, double *u, double *v, const cfdo_shape *shapes, int n);
+/* Colormaps::apply_colormap (colormaps.cpp:114-127) */
+void cfdo_apply_colormap(int colormap, float t, unsigned char *rgb);
+/* The pixel loop of update_field_texture (gui.cpp:1505-1561) without the GL upload: rgb = nx*ny*3 bytes. */
+void cfdo_render_rgb(int nx, int ny, double Lx, double Ly, const double *u, const double *v, const double *p, int field,
+                     int colormap, float scale_min, float scale_max, int normalize, float gamma, unsigned char *rgb);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,7 +2,7 @@
 //
 // TEST INFRASTRUCTURE ONLY (see cfdo_api.h).  This file contains no solver arithmetic of its own: it
 // includes the reference's public headers from /root/reference/src (never copied into this repo) and
-// forwards to the reference's functions.  oracle/Makefile compiles it together with the reference's
+// forwards to the reference's functions (two exceptions, marked RESTATED below: loops that live in the unbuildable gui.cpp).  oracle/Makefile compiles it together with the reference's
 // src/solver/{grid,bc,advection,diffusion,metrics,pressure,project,time_integrator}.cpp into
 // oracle/_ref/libcfdo_ref.so.  It mirrors the object set-up of the headless driver, main.cpp:104-130.
 #include "cfdo_api.h"
@@ -10,7 +10,15 @@
 #include <cstdio>
 #include <cstring>
 
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "colormaps.hpp"
+#include "gui/gui.hpp" // struct Shape (type-only stubs for the GUI toolkit headers: oracle/stubs/)
+#include "shapes.hpp"
 #include "solver/time_integrator.hpp"
+#include "viz.hpp"
 
 namespace {
 
@@ -73,6 +81,21 @@ struct View {
 struct UView : View { UView(const Grid &g, const double *d) : View(d, g.u_nx(), g.ny, g.u_pitch()) {} };
 struct VView : View { VView(const Grid &g, const double *d) : View(d, g.nx, g.v_ny(), g.v_pitch()) {} };
 struct PView : View { PView(const Grid &g, const double *d) : View(d, g.nx, g.ny, g.p_pitch()) {} };
+
+// A State whose u, v, p are views over caller memory (released, not freed, on scope exit).
+struct StateView {
+    State s;
+    static void view(Field2D<double> &f, const double *data, int NX, int NY, int pitch) {
+        f.nx = NX, f.ny = NY, f.pitch = pitch, f.ngx = 1, f.ngy = 1;
+        f.data = const_cast<double *>(data);
+    }
+    StateView(const Grid &g, const double *u, const double *v, const double *p) {
+        view(s.u, u, g.u_nx(), g.ny, g.u_pitch());
+        view(s.v, v, g.nx, g.v_ny(), g.v_pitch());
+        if (p) view(s.p, p, g.nx, g.ny, g.p_pitch());
+    }
+    ~StateView() { s.u.data = s.v.data = s.p.data = nullptr; }
+};
 
 } // namespace
 
@@ -227,6 +250,78 @@ void cfdo_sanitize(double *a, long n) {
     f.data = a;
     sanitize_field(f);
     f.data = nullptr;
+}
+
+// ---- readers / mutators around the step -------------------------------------------------
+void cfdo_compute_scalar(int nx, int ny, double Lx, double Ly, const double *u, const double *v, const double *p,
+                         int field, double *out, double *vmin, double *vmax) {
+    Grid g = make_grid(nx, ny, Lx, Ly);
+    StateView S(g, u, v, p);
+    std::vector<double> tmp;
+    compute_scalar(g, S.s, static_cast<ScalarField>(field), tmp, *vmin, *vmax); // viz.cpp:6-65
+    std::copy(tmp.begin(), tmp.end(), out);
+}
+// RESTATED from Gui::update_field_statistics, gui.cpp:1452-1474 (gui.cpp needs the GUI toolkit and does not build here)
+void cfdo_field_stats(const double *out, long n, double *mean, double *stddev) {
+    double sum = 0.0, sum_sq = 0.0;
+    int count = 0;
+    for (long k = 0; k < n; ++k) {
+        const double val = out[k];
+        if (std::isfinite(val)) {
+            sum += val;
+            sum_sq += val * val;
+            count++;
+        }
+    }
+    if (count > 0) {
+        *mean = sum / count;
+        double variance = (sum_sq / count) - (*mean * *mean);
+        *stddev = std::sqrt(std::max(0.0, variance));
+    } else {
+        *mean = 0.0;
+        *stddev = 0.0;
+    }
+}
+void cfdo_apply_shapes(int nx, int ny, double Lx, double Ly, double *u, double *v, const cfdo_shape *shapes, int n) {
+    Grid g = make_grid(nx, ny, Lx, Ly);
+    StateView S(g, u, v, nullptr);
+    std::vector<Shape> list;
+    for (int k = 0; k < n; ++k) {
+        Shape sh;
+        sh.type = shapes[k].type;
+        sh.pos = ImVec2(shapes[k].pos_x, shapes[k].pos_y);
+        sh.size = ImVec2(shapes[k].size_x, shapes[k].size_y);
+        sh.bcType = shapes[k].bc_type;
+        sh.enabled = shapes[k].enabled != 0;
+        list.push_back(sh);
+    }
+    apply_shape_boundary_conditions(g, S.s, list); // shapes.cpp:7-74
+}
+void cfdo_apply_colormap(int colormap, float t, unsigned char *rgb) {
+    Colormaps::apply_colormap(colormap, t, rgb[0], rgb[1], rgb[2]); // colormaps.cpp:114-127
+}
+// The pixel loop is RESTATED from update_field_texture, gui.cpp:1523-1551 (gui.cpp does not build here); the scalar field
+// and the colour come from the reference's own compute_scalar and Colormaps::apply_colormap.
+void cfdo_render_rgb(int nx, int ny, double Lx, double Ly, const double *u, const double *v, const double *p, int field,
+                     int colormap, float scale_min, float scale_max, int normalize, float gamma, unsigned char *rgb) {
+    Grid g = make_grid(nx, ny, Lx, Ly);
+    StateView S(g, u, v, p);
+    std::vector<double> tmp;
+    double vmin = 0.0, vmax = 0.0;
+    compute_scalar(g, S.s, static_cast<ScalarField>(field), tmp, vmin, vmax);
+    if (scale_min != 0.0f || scale_max != 1.0f) {
+        vmin = scale_min;
+        vmax = scale_max;
+    }
+    double scale = 1.0 / std::max(1e-6, vmax - vmin);
+    for (int idx = 0; idx < nx * ny; ++idx) {
+        double val = tmp[idx];
+        if (normalize) val = std::abs(val);
+        double norm = (val - vmin) * scale;
+        norm = std::clamp(norm, 0.0, 1.0);
+        norm = std::pow(norm, 1.0 / gamma);
+        Colormaps::apply_colormap(colormap, static_cast<float>(norm), rgb[3 * idx], rgb[3 * idx + 1], rgb[3 * idx + 2]);
+    }
 }
 
 } // extern "C"

@@ -165,3 +165,15 @@ def test_eager_drop_in_like_the_gui_loop(exe, port, tmp_path):
     assert np.linalg.norm(gp - p2) <= 1e-10 * np.linalg.norm(p2)
     gres, giters = lines[7].split()
     assert abs(float(gres) - res) <= 1e-8 * res and abs(int(giters) - iters) <= 1
+    # viz.hpp / shapes.hpp through the C++ layer (reference signatures)
+    su, sv = sim.u.copy(), sim.v.copy()
+    port.apply_shapes(nx, ny, Lx, Ly, su, sv, [cfdo.Shape(0, 30.0, 8.0, 9.0, 5.0, 0, 1), cfdo.Shape(1, 50.5, 20.25, 11.0, 11.0, 1, 1)])
+    assert same(load("s_u.bin", "u"), su) and same(load("s_v.bin", "v"), sv)
+    speed = port.compute_scalar(nx, ny, Lx, Ly, su, sv, sim.p, cfdo.FIELDS["speed"])
+    assert same(np.fromfile(tmp_path / "speed.bin").reshape(ny, nx), speed[0])
+    vort = port.compute_scalar(nx, ny, Lx, Ly, su, sv, sim.p, cfdo.FIELDS["vorticity"])
+    got = [float(x) for x in lines[8].split()]
+    assert got[0] == speed[1] and got[1] == speed[2] and got[2] == vort[1] and got[3] == vort[2]
+    assert abs(got[4] - vort[3]) <= 1e-12 * abs(vort[3]) + 1e-15 and abs(got[5] - vort[4]) <= 1e-10 * vort[4]
+    rgb = port.render_rgb(nx, ny, Lx, Ly, su, sv, sim.p, cfdo.FIELDS["speed"], 4)
+    assert np.array_equal(np.fromfile(tmp_path / "rgb.bin", dtype=np.uint8).reshape(ny, nx, 3), rgb)
