@@ -504,15 +504,27 @@ void enqueue_smooth(cfd_b200_solver *s, double tol, int finish) {
         static const int ry_env = getenv("CFD_B200_RB_RY") ? atoi(getenv("CFD_B200_RB_RY")) : 0;
         const int nstrips = cdiv(g.nx + 1, RS_OUT), gx = cdiv(nstrips, RS_WARPS);
         const int nrows = (g.top ? g.ny + 1 : g.ny) - (g.bottom ? 0 : 1) + 1;
-        // Rows per strip: 16 m + 1, so that the RY + 15 steps of a strip are whole turns of the 16-row ring.  15 rows of
-        // pipeline fill per strip: 257 on grids that fill the GPU (B200, 8192^2: RY 129 / 257 / 513 -> 0.46 / 0.42 / 0.50 ms
-        // per smooth), shorter strips to give every SM its 6 blocks, and when even 65-row strips leave SMs empty the
-        // tile kernel is the better one (1024^2: 21 us per smooth against 25).
+        // Rows per strip: 16 m + 1, so that the RY + 15 steps of a strip are whole turns of the 16-row ring.  Tall strips
+        // waste fewer steps on the pipeline fill, short ones give more blocks.  Cost model fitted on B200 (8192x1024 ...
+        // 16384x4096, scripts/strip_sweep.py): a block costs RY + 15 steps + ~12 steps of fixed overhead; the blocks run
+        // in rounds of 6 per SM, a full round at unit cost per step and a partly filled last round at 0.6 + 0.4 x fill
+        // (fewer resident warps hide less latency).  It picks the measured optimum in every case tried: 8192^2 -> 257,
+        // 8192x4096 -> 129, 8192x2048 / 4096^2 -> 257, 8192x1024 -> 129, 2048^2 -> 65.
         int RY = 257;
-        while (RY > 65 && (long long)gx * cdiv(nrows, RY) < 6LL * s->sm_count) RY = (RY - 1) / 2 + 1;
+        {
+            const double slots = 6.0 * s->sm_count;
+            double best = 1e300;
+            for (int ry = 257; ry >= 33; ry = (ry - 1) / 2 + 1) {
+                const double blocks = (double)gx * cdiv(nrows, ry);
+                const double full = std::floor(blocks / slots), rem = blocks - full * slots;
+                const double cost = (ry + 27) * (full + (rem > 0 ? 0.6 + 0.4 * rem / slots : 0.0));
+                if (cost < best) best = cost, RY = ry;
+            }
+        }
         const int forced = s->rb_strip > 0 ? s->rb_strip : ry_env;
         if (forced > 0) RY = forced;
         const dim3 grid(gx, cdiv(nrows, RY));
+        // too few blocks to fill the GPU: the tile kernel is the better one (1024^2: 21 us per smooth against 25)
         if (forced <= 0 && (long long)grid.x * grid.y < 3LL * s->sm_count) stream = false;
         else if (g.denom_pow2)
             launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<1>, grid, dim3(32 * RS_WARPS), RS_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, RY, nstrips, finish);
