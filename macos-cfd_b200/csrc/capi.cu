@@ -179,8 +179,9 @@ void stage_mark(cfd_b200_solver *s, int st) {
 // apply_bc_u / apply_bc_v / apply_bc_p in the reference's pass order (left/right, then bottom/top)
 void enqueue_bc(cfd_b200_solver *s, const BcD &bc, double *u, double *v, double *p, int sanitize) {
     const Geom &g = s->g;
-    LAUNCH(s, k_bc_lr, cdiv(g.ny + 5, 128), 128, g, bc, u, v, p, sanitize, s->d_sc);
-    if (g.bottom || g.top) LAUNCH(s, k_bc_bt, cdiv(g.nx + 3, 128), 128, g, bc, u, v, p, sanitize, s->d_sc);
+    const int nf = p ? 3 : 2; // blockIdx.y = field (u, v, p)
+    LAUNCH(s, k_bc_lr, dim3(cdiv(g.ny + 5, 128), nf), 128, g, bc, u, v, p, sanitize, s->d_sc);
+    if (g.bottom || g.top) LAUNCH(s, k_bc_bt, dim3(cdiv(g.nx + 3, 128), nf), 128, g, bc, u, v, p, sanitize, s->d_sc);
 }
 
 int reduce_fin(cfd_b200_solver *s, int kind, double tol, int max_iters);
