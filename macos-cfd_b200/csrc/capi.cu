@@ -90,6 +90,7 @@ struct cfd_b200_solver {
     P2PBlock *blk[P2P_MAXR] = {};
     unsigned long long halo_epoch = 0, red_epoch = 0;
     double *gathered = nullptr; // 4 doubles per rank (k_slab_pack / k_slab_unpack)
+    bool p_halo_sent = false;   // the solve already delivered the p row the projection reads (rode on its last reduction)
     bool halo_uv_valid = false; // the 2 halo rows of u, v are current (set by the exchange that ends a step)
     // V-cycle extension: coarse levels (level 0 aliases p / rhs), allocated on first use
     int mg_nlev = 0;
@@ -184,7 +185,7 @@ void enqueue_bc(cfd_b200_solver *s, const BcD &bc, double *u, double *v, double 
     if (g.bottom || g.top) LAUNCH(s, k_bc_bt, dim3(cdiv(g.nx + 3, 128), nf), 128, g, bc, u, v, p, sanitize, s->d_sc);
 }
 
-int reduce_fin(cfd_b200_solver *s, int kind, double tol, int max_iters);
+int reduce_fin(cfd_b200_solver *s, int kind, double tol, int max_iters, double *halo = nullptr, int rows = 0, int dirs = 0);
 
 void enqueue_cfl(cfd_b200_solver *s, double Re, double CFL, double dt_override, int cfl_only) {
     const Geom &g = s->g;
@@ -438,14 +439,38 @@ int allreduce(cfd_b200_solver *s, void *dev, int count, ncclRedOp_t op) {
 }
 // Row slabs: complete a grid-level reduction across ranks and run the scalar tail that consumes it (RED_* of p2p.cuh).
 // Peer-memory path: one fused kernel.  NCCL path: allreduce / all-gather + a one-thread tail kernel.
-int reduce_fin(cfd_b200_solver *s, int kind, double tol, int max_iters) {
+// `halo` != nullptr: `rows` rows of that field are exchanged (dirs as in halo_exchange) right behind the reduction --
+// in the same kernel on the peer-memory path, as a separate exchange on the NCCL path.
+int reduce_fin(cfd_b200_solver *s, int kind, double tol, int max_iters, double *halo, int rows, int dirs) {
     if (s->nranks == 1) return 0;
     if (s->p2p_on) {
         RedArgs a{};
         for (int r = 0; r < s->nranks; ++r) a.blk[r] = s->blk[r];
         a.nranks = s->nranks, a.rank = s->rank, a.kind = kind, a.epoch = ++s->red_epoch, a.tol = tol, a.max_iters = max_iters;
-        LAUNCH(s, k_p2p_reduce, 1, 32, a, s->d_sc);
+        if (halo) {
+            const Geom &g = s->g;
+            const int lower = g.bottom ? -1 : s->rank - 1, upper = g.top ? -1 : s->rank + 1;
+            const size_t fi = (size_t)(halo - s->arena) / s->n;
+            if (halo < s->arena || fi >= NFIELDS) return fail(CFD_B200_EINVAL, "halo exchange of a field outside the arena");
+            auto rowptr = [&](double *f, int jj) { return f + (size_t)(jj + CFD_YOFF) * g.P; };
+            auto peer_row = [&](int r, int jj) {
+                return static_cast<double *>(s->peer_arena[r]) + fi * s->peer_n[r] + (size_t)(jj + CFD_YOFF) * g.P;
+            };
+            a.count = (unsigned long long)rows * g.P;
+            a.hepoch = ++s->halo_epoch;
+            if (upper >= 0 && (dirs & HALO_UP)) a.job[a.njobs++] = HaloJob{rowptr(halo, g.ny - rows + 1), peer_row(upper, 1 - rows), 1};
+            if (lower >= 0 && (dirs & HALO_DOWN)) a.job[a.njobs++] = HaloJob{rowptr(halo, 1), peer_row(lower, s->peer_ny[lower] + 1), 0};
+            // both neighbours exchange flags even when rows travel one way only (uniform epochs)
+            if (lower >= 0) a.peer_data[0] = &s->blk[lower]->data_flag[1];
+            if (upper >= 0) a.peer_data[1] = &s->blk[upper]->data_flag[0];
+            a.halo = 1; // an end slab with nothing to send still signals and waits
+        }
+        LAUNCH(s, k_p2p_reduce, 1, P2P_RED_THREADS, a, s->d_sc);
         return 0;
+    }
+    if (halo) { // NCCL path: the reduction first, then the rows
+        TRY(reduce_fin(s, kind, tol, max_iters, nullptr, 0, 0));
+        return halo_exchange2(s, halo, nullptr, rows, dirs);
     }
     switch (kind) {
     case RED_PCG_INIT:
@@ -675,8 +700,7 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp, bool in_step = 
             LAUNCH(s, k_pcg_init, grid, PT_THREADS, g, s->rhs, s->r, s->d_sc, s->partials, pp->tol, pp->pcg_max_iters, single);
         }
         if (!single) {
-            TRY(reduce_fin(s, RED_PCG_INIT, pp->tol, pp->pcg_max_iters));
-            TRY(halo_exchange2(s, s->r, nullptr, 1, HALO_BOTH));
+            TRY(reduce_fin(s, RED_PCG_INIT, pp->tol, pp->pcg_max_iters, s->r, 1, HALO_BOTH));
         }
         const int ntx = cdiv(g.nx, PT_X), nty = cdiv(g.ny, PT_Y), ntiles = ntx * nty;
         const int grid = pcg_grid(s, ntiles);
@@ -705,8 +729,8 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp, bool in_step = 
                 LAUNCH(s, k_pcg_phase2, grid, PT_THREADS, g, s->p, s->r, s_new, s->d_sc, s->partials, ntx, ntiles, pp->tol,
                        pp->pcg_max_iters, single);
             if (!single) {
-                TRY(reduce_fin(s, RED_PCG2, pp->tol, pp->pcg_max_iters));
-                TRY(halo_exchange2(s, s->r, nullptr, 1, HALO_BOTH)); // the next direction update reads r one row out
+                // + r, 1 row both ways: the next direction update reads r one row out
+                TRY(reduce_fin(s, RED_PCG2, pp->tol, pp->pcg_max_iters, s->r, 1, HALO_BOTH));
             }
             double *t = s_old;
             s_old = s_new;
@@ -721,7 +745,11 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp, bool in_step = 
                 // 5 rows of p (and, once, of rhs: it is constant during the solve) for the redundant compute
                 if (!single) TRY(halo_exchange2(s, s->p, vc == 0 ? s->rhs : nullptr, RB_HY, HALO_BOTH));
                 enqueue_smooth(s, pp->tol, single);
-                if (!single) TRY(reduce_fin(s, RED_RBGS, pp->tol, 0));
+                // the residual sum; in a step the last one also carries the row of the new p that the projection of the
+                // slab above reads (time_integrator.cpp:188 follows directly)
+                const bool carry = in_step && vc == pp->vcycles - 1;
+                if (!single) TRY(reduce_fin(s, RED_RBGS, pp->tol, 0, carry ? s->p_alt : nullptr, 1, HALO_UP));
+                if (carry) s->p_halo_sent = true;
                 double *t = s->p;
                 s->p = s->p_alt;
                 s->p_alt = t;
@@ -787,9 +815,10 @@ int enqueue_step(cfd_b200_solver *s, const cfd_b200_bc *bc_in, double Re, double
     stage_mark(s, ST_DIV);
     enqueue_divergence(s, 1, 1); // :158-186
     stage_mark(s, ST_SOLVE);
+    s->p_halo_sent = false;
     int rc = enqueue_solve(s, pp, true); // :187
     if (rc) return rc;
-    TRY(halo_exchange2(s, s->p, nullptr, 1, HALO_UP)); // v faces of the bottom row read p one row below the slab
+    if (!s->p_halo_sent) TRY(halo_exchange2(s, s->p, nullptr, 1, HALO_UP)); // v faces of the bottom row read p one row below the slab
     stage_mark(s, ST_PROJECT);
     enqueue_project(s, s->d_sc, 0.0, 1, 1); // :188-202 (+ last_residual_ = isfinite(res) ? res : 1e9)
     stage_mark(s, ST_BC3);

@@ -127,9 +127,17 @@ struct RedArgs {
     unsigned long long epoch;
     double tol;
     int max_iters;
+    // optional: a halo exchange riding on the reduction (halo = 1).  The reduction is a barrier -- a rank that has seen
+    // every contribution knows that every rank has finished the kernels in front of its own contribution, i.e. has
+    // stopped reading its halo rows -- so the rows can be stored without the handshake of k_halo_xchg.
+    HaloJob job[2];
+    int halo, njobs; // halo = 1: flags are exchanged with both neighbours even if this rank has no rows to send
+    unsigned long long count, hepoch;
+    unsigned long long *peer_data[2];
 };
+#define P2P_RED_THREADS 256
 
-__global__ void __launch_bounds__(32) k_p2p_reduce(RedArgs a, Scalars *sc) { pdl_begin();
+__global__ void __launch_bounds__(P2P_RED_THREADS) k_p2p_reduce(RedArgs a, Scalars *sc) { pdl_begin();
     const int t = threadIdx.x, par = (int)(a.epoch & 1ull);
     P2PBlock *me = a.blk[a.rank];
     double v0, v1, v2 = 0.0, v3 = 0.0;
@@ -154,7 +162,7 @@ __global__ void __launch_bounds__(32) k_p2p_reduce(RedArgs a, Scalars *sc) { pdl
         p2p_wait(&me->red_flag[par][t], a.epoch, sc);
     }
     __syncthreads();
-    if (t != 0) return;
+    if (t == 0) {
     const bool is_max0 = a.kind == RED_STEP_END || a.kind == RED_CFL, is_max1 = is_max0 || a.kind == RED_DIAG;
     double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
     for (int r = 0; r < a.nranks; ++r) { // fixed rank order: bit-identical on every rank
@@ -179,5 +187,21 @@ __global__ void __launch_bounds__(32) k_p2p_reduce(RedArgs a, Scalars *sc) { pdl
     case RED_DIAG:
         sc->diag_sum = r0, sc->diag_max_bits = (unsigned long long)__double_as_longlong(r1);
         break;
+    }
+    } // t == 0
+    if (!a.halo) return;
+    // ---- the halo rows that ride along: store, fence, data flag, wait for the neighbours' rows
+    const size_t n2 = a.count / 2;
+    for (int j = 0; j < a.njobs; ++j) {
+        const double2 *src = reinterpret_cast<const double2 *>(a.job[j].src);
+        double2 *dst = reinterpret_cast<double2 *>(a.job[j].dst);
+#pragma unroll 4
+        for (size_t i = t; i < n2; i += blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < 2 && a.peer_data[t]) {
+        p2p_signal(a.peer_data[t], a.hepoch);
+        p2p_wait(&me->data_flag[t], a.hepoch, sc);
     }
 }
