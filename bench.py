@@ -267,7 +267,9 @@ def main():
             e1.record(stream)
             e1.synchronize()
             probe_ms.append(round(e0.elapsed_time(e1), 4))
-            if i.nonfinite or not math.isfinite(i.div_after) or not math.isfinite(i.div_before):
+            bad = bool(i.nonfinite) or not math.isfinite(i.div_after) or not math.isfinite(i.div_before)
+            # the sanitise flag is rank-local: every rank must leave the probe at the same step
+            if max_over_ranks(1.0 if bad else 0.0) > 0.0:
                 break
             clean += 1
         config["probe_ms_per_step_from_reset"] = probe_ms
