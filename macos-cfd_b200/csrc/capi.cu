@@ -520,6 +520,35 @@ void launch_fused(cfd_b200_solver *s, double tol, int ntx, int nty, int finish, 
         launch_kp(s, only_if_redo ? (s->pdl >> 2) & 1 : s->pdl & 1, k_rbgs_fused<POW2, 0>, dim3(grid), dim3(RB_THREADS), RB_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, ntx, ntiles, finish, only_if_redo);
 }
 
+// Strip height and grid of the streaming smoother for an nx-wide grid with `nrows` stored rows; false when the grid is
+// too small to fill the GPU with it (the caller then uses its tile / per-colour kernels).
+bool stream_plan(const cfd_b200_solver *s, int nx, int nrows, int *RY_out, int *gx_out, int *nstrips_out) {
+    static const int ry_env = getenv("CFD_B200_RB_RY") ? atoi(getenv("CFD_B200_RB_RY")) : 0;
+    const int nstrips = cdiv(nx + 1, RS_OUT), gx = cdiv(nstrips, RS_WARPS);
+    // Rows per strip: 16 m + 1, so that the RY + 15 steps of a strip are whole turns of the 16-row ring.  Tall strips
+    // waste fewer steps on the pipeline fill, short ones give more blocks.  Cost model fitted on B200 (8192x1024 ...
+    // 16384x4096, scripts/strip_sweep.py): a block costs RY + 15 steps + ~12 steps of fixed overhead; the blocks run
+    // in rounds of 6 per SM, a full round at unit cost per step and a partly filled last round at 0.6 + 0.4 x fill
+    // (fewer resident warps hide less latency).  It picks the measured optimum in every case tried: 8192^2 -> 257,
+    // 8192x4096 -> 129, 8192x2048 / 4096^2 -> 257, 8192x1024 -> 129, 2048^2 -> 65.
+    int RY = 257;
+    {
+        const double slots = 6.0 * s->sm_count;
+        double best = 1e300;
+        for (int ry = 257; ry >= 33; ry = (ry - 1) / 2 + 1) {
+            const double blocks = (double)gx * cdiv(nrows, ry);
+            const double full = std::floor(blocks / slots), rem = blocks - full * slots;
+            const double cost = (ry + 27) * (full + (rem > 0 ? 0.6 + 0.4 * rem / slots : 0.0));
+            if (cost < best) best = cost, RY = ry;
+        }
+    }
+    const int forced = s->rb_strip > 0 ? s->rb_strip : ry_env;
+    if (forced > 0) RY = forced;
+    *RY_out = RY, *gx_out = gx, *nstrips_out = nstrips;
+    // too few blocks to fill the GPU: the tile kernel is the better one (1024^2: 21 us per smooth against 25)
+    return forced > 0 || (long long)gx * cdiv(nrows, RY) >= 3LL * s->sm_count;
+}
+
 // One smooth() (pressure.cpp:64-111), p -> p_alt.  variant 1: the streaming kernel with the guarded tile kernel behind it
 // as its slow path (a no-op unless a non-finite value turned up); variant 2: the tile kernel alone.
 void enqueue_smooth(cfd_b200_solver *s, double tol, int finish) {
@@ -527,35 +556,16 @@ void enqueue_smooth(cfd_b200_solver *s, double tol, int finish) {
     const int ntx = cdiv(g.nx, RB_TX), nty = cdiv(g.ny, RB_TY);
     bool stream = s->variant == 1;
     if (stream) {
-        static const int ry_env = getenv("CFD_B200_RB_RY") ? atoi(getenv("CFD_B200_RB_RY")) : 0;
-        const int nstrips = cdiv(g.nx + 1, RS_OUT), gx = cdiv(nstrips, RS_WARPS);
         const int nrows = (g.top ? g.ny + 1 : g.ny) - (g.bottom ? 0 : 1) + 1;
-        // Rows per strip: 16 m + 1, so that the RY + 15 steps of a strip are whole turns of the 16-row ring.  Tall strips
-        // waste fewer steps on the pipeline fill, short ones give more blocks.  Cost model fitted on B200 (8192x1024 ...
-        // 16384x4096, scripts/strip_sweep.py): a block costs RY + 15 steps + ~12 steps of fixed overhead; the blocks run
-        // in rounds of 6 per SM, a full round at unit cost per step and a partly filled last round at 0.6 + 0.4 x fill
-        // (fewer resident warps hide less latency).  It picks the measured optimum in every case tried: 8192^2 -> 257,
-        // 8192x4096 -> 129, 8192x2048 / 4096^2 -> 257, 8192x1024 -> 129, 2048^2 -> 65.
-        int RY = 257;
-        {
-            const double slots = 6.0 * s->sm_count;
-            double best = 1e300;
-            for (int ry = 257; ry >= 33; ry = (ry - 1) / 2 + 1) {
-                const double blocks = (double)gx * cdiv(nrows, ry);
-                const double full = std::floor(blocks / slots), rem = blocks - full * slots;
-                const double cost = (ry + 27) * (full + (rem > 0 ? 0.6 + 0.4 * rem / slots : 0.0));
-                if (cost < best) best = cost, RY = ry;
-            }
-        }
-        const int forced = s->rb_strip > 0 ? s->rb_strip : ry_env;
-        if (forced > 0) RY = forced;
+        int RY, gx, nstrips;
+        stream = stream_plan(s, g.nx, nrows, &RY, &gx, &nstrips);
         const dim3 grid(gx, cdiv(nrows, RY));
-        // too few blocks to fill the GPU: the tile kernel is the better one (1024^2: 21 us per smooth against 25)
-        if (forced <= 0 && (long long)grid.x * grid.y < 3LL * s->sm_count) stream = false;
-        else if (g.denom_pow2)
-            launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<1>, grid, dim3(32 * RS_WARPS), RS_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, RY, nstrips, finish);
+        if (!stream) {
+            // too small for the streaming kernel: the tile kernel below runs on its own
+        } else if (g.denom_pow2)
+            launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<1, 0>, grid, dim3(32 * RS_WARPS), RS_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, RY, nstrips, finish);
         else
-            launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<0>, grid, dim3(32 * RS_WARPS), RS_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, RY, nstrips, finish);
+            launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<0, 0>, grid, dim3(32 * RS_WARPS), RS_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, RY, nstrips, finish);
     }
     if (g.denom_pow2) launch_fused<1>(s, tol, ntx, nty, finish, stream);
     else launch_fused<0>(s, tol, ntx, nty, finish, stream);
@@ -577,13 +587,15 @@ int enqueue_vcycle(cfd_b200_solver *s, const cfd_b200_params *pp, double Lx, dou
         MgLevel &L = s->mg[l];
         const int nx = g.nx >> l, ny = g.ny >> l;
         if (l > 0 && (L.nx != nx || L.ny != ny || !L.p)) {
-            if (L.p) cudaFree(L.p), cudaFree(L.rhs);
+            if (L.p) cudaFree(L.p), cudaFree(L.rhs), cudaFree(L.alt);
             L.P = ((nx + 3 + CFD_XOFF + 2) + 15) / 16 * 16;
             const size_t n = (size_t)L.P * (ny + 3 + 2 * CFD_YOFF);
             CU(cudaMalloc(&L.p, n * sizeof(double)));
             CU(cudaMalloc(&L.rhs, n * sizeof(double)));
+            CU(cudaMalloc(&L.alt, n * sizeof(double))); // ping-pong partner of p for the streaming sweeps
             CU(cudaMemsetAsync(L.p, 0, n * sizeof(double), s->stream));
             CU(cudaMemsetAsync(L.rhs, 0, n * sizeof(double), s->stream));
+            CU(cudaMemsetAsync(L.alt, 0, n * sizeof(double), s->stream));
         }
         L.nx = nx;
         L.ny = ny;
@@ -591,7 +603,7 @@ int enqueue_vcycle(cfd_b200_solver *s, const cfd_b200_params *pp, double Lx, dou
         L.idx2 = 1.0 / (dx * dx);
         L.idy2 = 1.0 / (dy * dy);
         L.denom = 2.0 * (L.idx2 + L.idy2);
-        if (l == 0) L.P = g.P, L.p = s->p, L.rhs = s->rhs;
+        if (l == 0) L.P = g.P, L.p = s->p, L.rhs = s->rhs, L.alt = s->p_alt;
     }
     if (nlev > s->mg_nlev) s->mg_nlev = nlev;
     // first level that (with everything below it) fits into one block's shared memory
@@ -623,7 +635,29 @@ int enqueue_vcycle(cfd_b200_solver *s, const cfd_b200_params *pp, double Lx, dou
             s->mg_cta_smem_max = cta_smem;
         }
     }
-    auto smooth = [&](const MgLevel &L, int n) {
+    // n red-black sweeps on level l.  Levels that fill the GPU take two sweeps per launch with the streaming smoother
+    // (k_rbgs_stream<., 1>: the four colour passes of two sweeps in one pass over the level, p ping-ponged); the others,
+    // and an odd sweep, take one launch per colour.
+    auto smooth = [&](int l, int n) {
+        MgLevel &L = s->mg[l];
+        int RY = 0, gx = 0, nstrips = 0;
+        if (s->variant == 1 && n >= 2 && stream_plan(s, L.nx, L.ny + 2, &RY, &gx, &nstrips)) {
+            Geom lg{};
+            lg.nx = L.nx, lg.ny = L.ny, lg.ny_glob = L.ny, lg.P = L.P, lg.j0 = 0, lg.bottom = lg.top = 1;
+            lg.idx2 = L.idx2, lg.idy2 = L.idy2, lg.denom = L.denom, lg.inv_denom = 1.0 / L.denom;
+            int e = 0;
+            const bool pow2 = std::frexp(L.denom, &e) == 0.5;
+            const dim3 grid(gx, cdiv(L.ny + 2, RY));
+            for (; n >= 2; n -= 2) {
+                if (pow2)
+                    launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<1, 1>, grid, dim3(32 * RS_WARPS), RS_SMEM, lg, L.p, L.alt, L.rhs, s->d_sc, s->partials, 0.0, RY, nstrips, 0);
+                else
+                    launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<0, 1>, grid, dim3(32 * RS_WARPS), RS_SMEM, lg, L.p, L.alt, L.rhs, s->d_sc, s->partials, 0.0, RY, nstrips, 0);
+                double *t = L.p;
+                L.p = L.alt, L.alt = t;
+                if (l == 0) s->p = L.p, s->p_alt = L.alt; // level 0 aliases the State's pressure
+            }
+        }
         dim3 block(32, 8), grid(cdiv(cdiv(L.nx + 1, 2), 32), cdiv(L.ny, 8));
         for (int k = 0; k < n; ++k)
             for (int colour = 0; colour < 2; ++colour) LAUNCH(s, k_mg_colour, grid, block, L, colour, s->d_sc);
@@ -633,19 +667,19 @@ int enqueue_vcycle(cfd_b200_solver *s, const cfd_b200_params *pp, double Lx, dou
     const int top = lc < nlev ? lc : nlev - 1; // levels [0, top) run as global-memory kernels on the way down
     for (int vc = 0; vc < pp->vcycles; ++vc) {
         for (int l = 0; l < top; ++l) {
-            smooth(s->mg[l], sweeps);
+            smooth(l, sweeps);
             const MgLevel &C = s->mg[l + 1];
             LAUNCH(s, k_mg_restrict, dim3(cdiv(C.nx, 32), cdiv(C.ny, 8)), dim3(32, 8), s->mg[l], C, s->d_sc);
         }
         if (lc < nlev) {
             launch_k(s, k_mg_coarse_cta, dim3(1), dim3(1024), (size_t)cta_smem, s->mg[lc], plan, s->d_sc);
         } else {
-            smooth(s->mg[nlev - 1], nlev == 1 ? sweeps : 16 * sweeps);
+            smooth(nlev - 1, nlev == 1 ? sweeps : 16 * sweeps);
         }
         for (int l = top - 1; l >= 0; --l) {
             const MgLevel &F = s->mg[l];
             LAUNCH(s, k_mg_prolong, dim3(cdiv(F.nx, 32), cdiv(F.ny, 8)), dim3(32, 8), F, s->mg[l + 1], s->d_sc);
-            smooth(F, sweeps);
+            smooth(l, sweeps);
         }
         dim3 rgrid(cdiv(g.nx, 256), g.ny < 256 ? g.ny : 256);
         LAUNCH(s, k_mg_residual_norm, rgrid, 256, s->mg[0], s->d_sc, s->partials, pp->tol);
@@ -985,8 +1019,10 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
             rc = fail(CFD_B200_ECUDA, "cudaFuncSetAttribute(k_rbgs_fused) failed: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }
-        cudaFuncSetAttribute(k_rbgs_stream<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k_rbgs_stream<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_rbgs_stream<0, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_rbgs_stream<1, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_rbgs_stream<0, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_rbgs_stream<1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (cudaMalloc(&s->partials, s->partials_n * sizeof(double)) != cudaSuccess) { rc = fail(CFD_B200_ENOMEM, "partials alloc failed"); break; }
         for (int i = 0; i < ST_COUNT; ++i)
             if (cudaEventCreate(&s->ev[i]) != cudaSuccess) { rc = fail(CFD_B200_ECUDA, "event create failed"); break; }
@@ -1032,6 +1068,7 @@ void cfd_b200_destroy(cfd_b200_solver *s) {
     for (int l = 1; l < s->mg_nlev; ++l) {
         if (s->mg[l].p) cudaFree(s->mg[l].p);
         if (s->mg[l].rhs) cudaFree(s->mg[l].rhs);
+        if (s->mg[l].alt) cudaFree(s->mg[l].alt);
     }
     if (s->viz_rgb) cudaFree(s->viz_rgb);
     double *fields[] = {s->arena, s->scratch_u, s->scratch_v, s->partials, s->viz_out};

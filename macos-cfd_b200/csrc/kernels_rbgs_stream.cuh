@@ -56,7 +56,10 @@ __device__ __forceinline__ void rs_cp8(double *smem, const double *gmem) {
 __device__ __forceinline__ void rs_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void rs_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int POW2>
+// VC = 0: smooth() of the reference (above).  VC = 1: two red-black sweeps of the true V-cycle extension
+// (kernels_vcycle.cuh: k_mg_colour x 4 in one launch): p = (sum - rhs) / (denom + wall), where `wall` moves the p = 0
+// condition onto the wall faces of boundary cells; no isfinite guards in that algorithm, no residual, ghost ring = 0.
+template <int POW2, int VC>
 __global__ void __launch_bounds__(32 * RS_WARPS, 6)
     k_rbgs_stream(Geom g, const double *__restrict__ pin, double *__restrict__ pout, const double *__restrict__ rhs,
                   Scalars *sc, double *partials, double tol, int RY, int nstrips, int finish) { pdl_begin();
@@ -111,6 +114,8 @@ __global__ void __launch_bounds__(32 * RS_WARPS, 6)
             const double *const Bh[2] = {ringp + (E0 ? lbR : lbL), ringp + (E1 ? lbR : lbL)}; // its neighbour in the adjacent lane's pair
             const double *const Ro[2] = {ringr + lb + E0, ringr + lb + E1};
             const bool colok[2] = {E0 ? c1 : c0, E1 ? c1 : c0};
+            // VC: the wall term of mg_wall(), column part, for the point with column offset E[x]
+            const double wxv[2] = {(double)((a + E0 == 1) + (a + E0 == g.nx)) * idx2, (double)((a + E1 == 1) + (a + E1 == g.nx)) * idx2};
             const int t_jlo = jlo - ys, t_jhi = jhi - ys;                  // updatable relative rows
             const int t_st0 = y0 - ys, t_st1 = y1 - ys;                    // stored relative rows
             const int rr_first = max(y0, 1) - ys, rr_last = min(y1, g.ny) - ys; // residual rows (relative)
@@ -160,7 +165,16 @@ __global__ void __launch_bounds__(32 * RS_WARPS, 6)
                         const double ph = Bh[x][S * RS_ROW];          // the horizontal neighbour in the adjacent lane's pair
                         const double rv = Ro[x][S * RS_ROW];
                         const double sum = (ph + ho[k]) * idx2 + (pt + bo[k]) * idy2;
-                        double xv = POW2 ? (rv + sum) * g.inv_denom : (rv + sum) / g.denom;
+                        double xv;
+                        if (VC) { // kernels_vcycle.cuh, k_mg_colour: (sum - rhs) / (denom + mg_wall)
+                            const int jj = ys + rt;
+                            const double wall = wxv[x] + (double)((jj == 1) + (jj == g.ny)) * idy2;
+                            const double num = sum - rv;
+                            xv = POW2 ? num * g.inv_denom : num / g.denom; // wall = 0: denom + 0.0 is denom
+                            if (wall != 0.0) xv = num / (g.denom + wall);
+                        } else {
+                            xv = POW2 ? (rv + sum) * g.inv_denom : (rv + sum) / g.denom;
+                        }
                         const bool ok = (!FILL || rt >= t_jlo) && rt <= t_jhi && colok[x];
                         if (ok) Bo[x][S * RS_ROW] = xv;
                         if (k == 3) {                                  // row rt is final: the lane's pair, column order
@@ -169,7 +183,7 @@ __global__ void __launch_bounds__(32 * RS_WARPS, 6)
                             cur[0] = e ? ho[k] : xv;
                             cur[1] = e ? xv : ho[k];
                             if (rt >= t_st0 && rt <= t_st1 && st_lane) {
-                                xbits = max(xbits, max(__double2hiint(cur[0]) & 0x7ff00000, __double2hiint(cur[1]) & 0x7ff00000));
+                                if (!VC) xbits = max(xbits, max(__double2hiint(cur[0]) & 0x7ff00000, __double2hiint(cur[1]) & 0x7ff00000));
                                 *reinterpret_cast<double2 *>(po) = make_double2(cur[0], cur[1]);
                             }
                         }
@@ -180,7 +194,7 @@ __global__ void __launch_bounds__(32 * RS_WARPS, 6)
                     // ---- residual (pressure.cpp:96-110) in relative row rr = t-9: r = rhs - L p, sum of r^2.  Rows
                     //      rr-1, rr, rr+1 of the lane's own columns are pass 3's last three results (registers).
                     const int rr = t - 9;
-                    if ((!FILL || rr >= rr_first) && rr <= rr_last) {
+                    if (!VC && (!FILL || rr >= rr_first) && rr <= rr_last) {
                         const int SR = (u - 9) & (RS_R - 1);
                         const double hl = ringp[SR * RS_ROW + lbL];    // column a - 1
                         const double hr = ringp[SR * RS_ROW + lbR];    // column a + 2
@@ -204,7 +218,7 @@ __global__ void __launch_bounds__(32 * RS_WARPS, 6)
             rs_wait<0>();
         }
     }
-    if (done) return;
+    if (done || VC) return;
     if (redo) *reinterpret_cast<volatile int *>(&sc->rb_redo) = 1;
     grid_sum<1>(acc, partials, &sc->ticket[2], [=](double(&t)[1]) {
         if (*reinterpret_cast<volatile int *>(&sc->rb_redo)) return; // the guarded kernel behind us redoes this smooth()

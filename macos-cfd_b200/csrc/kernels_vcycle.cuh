@@ -16,6 +16,7 @@ struct MgLevel {
     int nx, ny, P;
     double idx2, idy2, denom;
     double *p, *rhs; // device arrays in the common padded layout (ghost ring = 0)
+    double *alt;     // ping-pong partner of p (streaming sweeps); level 0: the State's p_alt
 };
 __host__ __device__ __forceinline__ size_t mg_idx(const MgLevel &L, int ii, int jj) {
     return (size_t)(jj + CFD_YOFF) * (size_t)L.P + (size_t)(ii + CFD_XOFF);
