@@ -563,9 +563,9 @@ void enqueue_smooth(cfd_b200_solver *s, double tol, int finish) {
         if (!stream) {
             // too small for the streaming kernel: the tile kernel below runs on its own
         } else if (g.denom_pow2)
-            launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<1, 0>, grid, dim3(32 * RS_WARPS), RS_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, RY, nstrips, finish);
+            launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<1, 0>, grid, dim3(32 * RS_WARPS), RS_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, RY, nstrips, finish, RsCoarse{});
         else
-            launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<0, 0>, grid, dim3(32 * RS_WARPS), RS_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, RY, nstrips, finish);
+            launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<0, 0>, grid, dim3(32 * RS_WARPS), RS_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, RY, nstrips, finish, RsCoarse{});
     }
     if (g.denom_pow2) launch_fused<1>(s, tol, ntx, nty, finish, stream);
     else launch_fused<0>(s, tol, ntx, nty, finish, stream);
@@ -635,54 +635,69 @@ int enqueue_vcycle(cfd_b200_solver *s, const cfd_b200_params *pp, double Lx, dou
             s->mg_cta_smem_max = cta_smem;
         }
     }
-    // n red-black sweeps on level l.  Levels that fill the GPU take two sweeps per launch with the streaming smoother
-    // (k_rbgs_stream<., 1>: the four colour passes of two sweeps in one pass over the level, p ping-ponged); the others,
-    // and an odd sweep, take one launch per colour.
-    auto smooth = [&](int l, int n) {
+    // n red-black sweeps on level l, followed by `then`: RS_VC_RESTRICT (residual restricted to level l+1, its p zeroed)
+    // or RS_VC_NORM (residual norm of the level + the cycle loop's exit test).  Levels that fill the GPU take two sweeps
+    // per launch with the streaming smoother (k_rbgs_stream<., 1>: the four colour passes of two sweeps in one pass over
+    // the level, p ping-ponged) and the last such launch does `then` in its residual stage; an odd sweep goes first, one
+    // launch per colour like every sweep of a small level, and `then` is a kernel of its own.
+    auto smooth = [&](int l, int n, int then) {
         MgLevel &L = s->mg[l];
+        dim3 block(32, 8), cgrid(cdiv(cdiv(L.nx + 1, 2), 32), cdiv(L.ny, 8));
+        auto colour_sweeps = [&](int k) {
+            for (; k > 0; --k)
+                for (int colour = 0; colour < 2; ++colour) LAUNCH(s, k_mg_colour, cgrid, block, L, colour, s->d_sc);
+        };
         int RY = 0, gx = 0, nstrips = 0;
-        if (s->variant == 1 && n >= 2 && stream_plan(s, L.nx, L.ny + 2, &RY, &gx, &nstrips)) {
+        const bool stream = s->variant == 1 && n >= 2 && L.nx % 2 == 0 && L.ny % 2 == 0 &&
+                            stream_plan(s, L.nx, L.ny + 2, &RY, &gx, &nstrips);
+        if (stream) {
+            colour_sweeps(n & 1);
             Geom lg{};
             lg.nx = L.nx, lg.ny = L.ny, lg.ny_glob = L.ny, lg.P = L.P, lg.j0 = 0, lg.bottom = lg.top = 1;
             lg.idx2 = L.idx2, lg.idy2 = L.idy2, lg.denom = L.denom, lg.inv_denom = 1.0 / L.denom;
             int e = 0;
             const bool pow2 = std::frexp(L.denom, &e) == 0.5;
-            const dim3 grid(gx, cdiv(L.ny + 2, RY));
-            for (; n >= 2; n -= 2) {
+            const int ry = RY - 1; // even: strips start at odd rows (see the kernel)
+            const dim3 grid(gx, cdiv(L.ny + 1, ry));
+            RsCoarse cz{};
+            if (then == RS_VC_RESTRICT) cz = RsCoarse{s->mg[l + 1].rhs, s->mg[l + 1].p, s->mg[l + 1].P};
+            for (int k = n / 2; k > 0; --k) {
+                const int fin = k == 1 ? then : RS_VC_SMOOTH;
                 if (pow2)
-                    launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<1, 1>, grid, dim3(32 * RS_WARPS), RS_SMEM, lg, L.p, L.alt, L.rhs, s->d_sc, s->partials, 0.0, RY, nstrips, 0);
+                    launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<1, 1>, grid, dim3(32 * RS_WARPS), RS_SMEM, lg, L.p, L.alt, L.rhs, s->d_sc, s->partials, pp->tol, ry, nstrips, fin, cz);
                 else
-                    launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<0, 1>, grid, dim3(32 * RS_WARPS), RS_SMEM, lg, L.p, L.alt, L.rhs, s->d_sc, s->partials, 0.0, RY, nstrips, 0);
+                    launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<0, 1>, grid, dim3(32 * RS_WARPS), RS_SMEM, lg, L.p, L.alt, L.rhs, s->d_sc, s->partials, pp->tol, ry, nstrips, fin, cz);
                 double *t = L.p;
                 L.p = L.alt, L.alt = t;
                 if (l == 0) s->p = L.p, s->p_alt = L.alt; // level 0 aliases the State's pressure
             }
+        } else {
+            colour_sweeps(n);
         }
-        dim3 block(32, 8), grid(cdiv(cdiv(L.nx + 1, 2), 32), cdiv(L.ny, 8));
-        for (int k = 0; k < n; ++k)
-            for (int colour = 0; colour < 2; ++colour) LAUNCH(s, k_mg_colour, grid, block, L, colour, s->d_sc);
+        if (stream || then == RS_VC_SMOOTH) return;
+        if (then == RS_VC_RESTRICT) {
+            const MgLevel &C = s->mg[l + 1];
+            LAUNCH(s, k_mg_restrict, dim3(cdiv(C.nx, 32), cdiv(C.ny, 8)), dim3(32, 8), L, C, s->d_sc);
+        } else {
+            dim3 rgrid(cdiv(L.nx, 256), L.ny < 256 ? L.ny : 256);
+            LAUNCH(s, k_mg_residual_norm, rgrid, 256, L, s->d_sc, s->partials, pp->tol);
+        }
     };
     if (!in_step) LAUNCH(s, k_solve_begin, 1, 1, s->d_sc);
     LAUNCH(s, k_mg_zero_ghosts, cdiv((g.nx > g.ny ? g.nx : g.ny) + 2, 128), 128, s->mg[0], s->d_sc);
     const int top = lc < nlev ? lc : nlev - 1; // levels [0, top) run as global-memory kernels on the way down
     for (int vc = 0; vc < pp->vcycles; ++vc) {
-        for (int l = 0; l < top; ++l) {
-            smooth(l, sweeps);
-            const MgLevel &C = s->mg[l + 1];
-            LAUNCH(s, k_mg_restrict, dim3(cdiv(C.nx, 32), cdiv(C.ny, 8)), dim3(32, 8), s->mg[l], C, s->d_sc);
-        }
+        for (int l = 0; l < top; ++l) smooth(l, sweeps, RS_VC_RESTRICT);
         if (lc < nlev) {
             launch_k(s, k_mg_coarse_cta, dim3(1), dim3(1024), (size_t)cta_smem, s->mg[lc], plan, s->d_sc);
         } else {
-            smooth(nlev - 1, nlev == 1 ? sweeps : 16 * sweeps);
+            smooth(nlev - 1, nlev == 1 ? sweeps : 16 * sweeps, top == 0 ? RS_VC_NORM : RS_VC_SMOOTH);
         }
         for (int l = top - 1; l >= 0; --l) {
             const MgLevel &F = s->mg[l];
             LAUNCH(s, k_mg_prolong, dim3(cdiv(F.nx, 32), cdiv(F.ny, 8)), dim3(32, 8), F, s->mg[l + 1], s->d_sc);
-            smooth(l, sweeps);
+            smooth(l, sweeps, l == 0 ? RS_VC_NORM : RS_VC_SMOOTH);
         }
-        dim3 rgrid(cdiv(g.nx, 256), g.ny < 256 ? g.ny : 256);
-        LAUNCH(s, k_mg_residual_norm, rgrid, 256, s->mg[0], s->d_sc, s->partials, pp->tol);
     }
     if (!in_step) LAUNCH(s, k_solve_finish, 1, 1, s->d_sc);
     return 0;

@@ -58,11 +58,20 @@ template <int N> __device__ __forceinline__ void rs_wait() { asm volatile("cp.as
 
 // VC = 0: smooth() of the reference (above).  VC = 1: two red-black sweeps of the true V-cycle extension
 // (kernels_vcycle.cuh: k_mg_colour x 4 in one launch): p = (sum - rhs) / (denom + wall), where `wall` moves the p = 0
-// condition onto the wall faces of boundary cells; no isfinite guards in that algorithm, no residual, ghost ring = 0.
+// condition onto the wall faces of boundary cells; no isfinite guards in that algorithm, ghost ring = 0.  What follows the
+// sweeps in the cycle rides on the residual stage (`finish`): RS_VC_RESTRICT = residual + 4-cell-mean restriction to the
+// coarse right-hand side + coarse initial guess 0 (k_mg_restrict), RS_VC_NORM = ||rhs - L p||_2 and the cycle loop's
+// exit test (k_mg_residual_norm).  Strips then start at odd rows and hold an even number of rows (a 2x2 block of fine
+// cells never straddles two strips).
+enum { RS_VC_SMOOTH = 0, RS_VC_RESTRICT = 1, RS_VC_NORM = 2 };
+struct RsCoarse {
+    double *rhs, *p; // coarse level arrays (common padded layout)
+    int P;
+};
 template <int POW2, int VC>
 __global__ void __launch_bounds__(32 * RS_WARPS, 6)
     k_rbgs_stream(Geom g, const double *__restrict__ pin, double *__restrict__ pout, const double *__restrict__ rhs,
-                  Scalars *sc, double *partials, double tol, int RY, int nstrips, int finish) { pdl_begin();
+                  Scalars *sc, double *partials, double tol, int RY, int nstrips, int finish, RsCoarse cz) { pdl_begin();
     extern __shared__ double rs_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     double *ringp = rs_raw + w * RS_WDOUBLES + 2;   // [slot][RS_ROW]
@@ -76,7 +85,8 @@ __global__ void __launch_bounds__(32 * RS_WARPS, 6)
         const int a = X0 + 2 * lane;            // this lane's columns: a, a + 1
         // rows this launch stores: the slab's cell rows plus the ghost rows the slab owns (carried over unchanged)
         const int ylo = g.bottom ? 0 : 1, yhi = g.top ? g.ny + 1 : g.ny;
-        const int y0 = ylo + blockIdx.y * RY, y1 = min(y0 + RY - 1, yhi);
+        const int y0 = VC ? (blockIdx.y ? 1 + (int)blockIdx.y * RY : 0) : ylo + blockIdx.y * RY;
+        const int y1 = VC ? min(((int)blockIdx.y + 1) * RY, yhi) : min(y0 + RY - 1, yhi);
         // rows that may be updated: cells of this slab and, towards a neighbouring slab, its exchanged halo rows
         const int jlo = g.bottom ? 1 : 1 - RS_HY + 1, jhi = g.top ? g.ny : g.ny + RS_HY - 1;
         const bool c0 = a >= 1 && a <= g.nx, c1 = a + 1 >= 1 && a + 1 <= g.nx; // interior columns
@@ -116,6 +126,8 @@ __global__ void __launch_bounds__(32 * RS_WARPS, 6)
             const bool colok[2] = {E0 ? c1 : c0, E1 ? c1 : c0};
             // VC: the wall term of mg_wall(), column part, for the point with column offset E[x]
             const double wxv[2] = {(double)((a + E0 == 1) + (a + E0 == g.nx)) * idx2, (double)((a + E1 == 1) + (a + E1 == g.nx)) * idx2};
+            const double wxc[2] = {(double)((a == 1) + (a == g.nx)) * idx2, (double)((a + 1 == 1) + (a + 1 == g.nx)) * idx2}; // by column
+            double sprev = 0.0; // RS_VC_RESTRICT: residual sum of the pair's columns in the odd row of a 2x2 block
             const int t_jlo = jlo - ys, t_jhi = jhi - ys;                  // updatable relative rows
             const int t_st0 = y0 - ys, t_st1 = y1 - ys;                    // stored relative rows
             const int rr_first = max(y0, 1) - ys, rr_last = min(y1, g.ny) - ys; // residual rows (relative)
@@ -194,6 +206,30 @@ __global__ void __launch_bounds__(32 * RS_WARPS, 6)
                     // ---- residual (pressure.cpp:96-110) in relative row rr = t-9: r = rhs - L p, sum of r^2.  Rows
                     //      rr-1, rr, rr+1 of the lane's own columns are pass 3's last three results (registers).
                     const int rr = t - 9;
+                    if (VC && finish != RS_VC_SMOOTH && (!FILL || rr >= rr_first) && rr <= rr_last) {
+                        // kernels_vcycle.cuh, mg_resid: rhs - (L p - wall p), then k_mg_restrict / k_mg_residual_norm
+                        const int SR = (u - 9) & (RS_R - 1), jj = ys + rr;
+                        const double hl = ringp[SR * RS_ROW + lbL], hr = ringp[SR * RS_ROW + lbR];
+                        const double rhA = ringr[SR * RS_ROW + lb], rhB = ringr[SR * RS_ROW + lb + 1];
+                        const double wy = (double)((jj == 1) + (jj == g.ny)) * idy2;
+                        double ApA = (r2[1] - 2.0 * r2[0] + hl) * idx2 + (r1[0] - 2.0 * r2[0] + r3[0]) * idy2;
+                        double ApB = (hr - 2.0 * r2[1] + r2[0]) * idx2 + (r1[1] - 2.0 * r2[1] + r3[1]) * idy2;
+                        ApA = ApA - (wxc[0] + wy) * r2[0];
+                        ApB = ApB - (wxc[1] + wy) * r2[1];
+                        const double resA = rhA - ApA, resB = rhB - ApB;
+                        if (finish == RS_VC_NORM) {
+                            acc[0] += inA ? resA * resA : 0.0;
+                            acc[0] += inB ? resB * resB : 0.0;
+                        } else {
+                            const double srow = resA + resB;
+                            if (!(jj & 1) && inA) { // second row of the block: coarse cell ((a + 1) / 2, jj / 2)
+                                const size_t oc = (size_t)(jj / 2 + CFD_YOFF) * cz.P + ((a + 1) / 2 + CFD_XOFF);
+                                cz.rhs[oc] = 0.25 * (sprev + srow);
+                                cz.p[oc] = 0.0;
+                            }
+                            sprev = srow;
+                        }
+                    }
                     if (!VC && (!FILL || rr >= rr_first) && rr <= rr_last) {
                         const int SR = (u - 9) & (RS_R - 1);
                         const double hl = ringp[SR * RS_ROW + lbL];    // column a - 1
@@ -218,7 +254,16 @@ __global__ void __launch_bounds__(32 * RS_WARPS, 6)
             rs_wait<0>();
         }
     }
-    if (done || VC) return;
+    if (done || (VC && finish != RS_VC_NORM)) return;
+    if (VC) { // k_mg_residual_norm's tail
+        grid_sum<1>(acc, partials, &sc->ticket[2], [=](double(&t)[1]) {
+            const double res = sqrt(t[0]);
+            sc->res = res;
+            sc->iters = sc->iters + 1;
+            if (res < tol) sc->done = 1;
+        });
+        return;
+    }
     if (redo) *reinterpret_cast<volatile int *>(&sc->rb_redo) = 1;
     grid_sum<1>(acc, partials, &sc->ticket[2], [=](double(&t)[1]) {
         if (*reinterpret_cast<volatile int *>(&sc->rb_redo)) return; // the guarded kernel behind us redoes this smooth()
