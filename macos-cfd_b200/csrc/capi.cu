@@ -533,7 +533,7 @@ bool stream_plan(const cfd_b200_solver *s, int nx, int nrows, int *RY_out, int *
     // 8192x4096 -> 129, 8192x2048 / 4096^2 -> 257, 8192x1024 -> 129, 2048^2 -> 65.
     int RY = 257;
     {
-        const double slots = 6.0 * s->sm_count;
+        const double slots = (double)RS_BLOCKS_PER_SM * s->sm_count;
         double best = 1e300;
         for (int ry = 257; ry >= 33; ry = (ry - 1) / 2 + 1) {
             const double blocks = (double)gx * cdiv(nrows, ry);
@@ -546,7 +546,7 @@ bool stream_plan(const cfd_b200_solver *s, int nx, int nrows, int *RY_out, int *
     if (forced > 0) RY = forced;
     *RY_out = RY, *gx_out = gx, *nstrips_out = nstrips;
     // too few blocks to fill the GPU: the tile kernel is the better one (1024^2: 21 us per smooth against 25)
-    return forced > 0 || (long long)gx * cdiv(nrows, RY) >= 3LL * s->sm_count;
+    return forced > 0 || (long long)gx * cdiv(nrows, RY) * RS_WARPS >= 6LL * s->sm_count;
 }
 
 // One smooth() (pressure.cpp:64-111), p -> p_alt.  variant 1: the streaming kernel with the guarded tile kernel behind it
@@ -1034,10 +1034,16 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
             rc = fail(CFD_B200_ECUDA, "cudaFuncSetAttribute(k_rbgs_fused) failed: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }
-        cudaFuncSetAttribute(k_rbgs_stream<0, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k_rbgs_stream<1, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k_rbgs_stream<0, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k_rbgs_stream<1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        {
+            auto prep = [](auto kernel) {
+                return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
+                       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM) == cudaSuccess;
+            };
+            if (!prep(k_rbgs_stream<0, 0>) || !prep(k_rbgs_stream<1, 0>) || !prep(k_rbgs_stream<0, 1>) || !prep(k_rbgs_stream<1, 1>)) {
+                rc = fail(CFD_B200_ECUDA, "cudaFuncSetAttribute(k_rbgs_stream) failed: %s", cudaGetErrorString(cudaGetLastError()));
+                break;
+            }
+        }
         if (cudaMalloc(&s->partials, s->partials_n * sizeof(double)) != cudaSuccess) { rc = fail(CFD_B200_ENOMEM, "partials alloc failed"); break; }
         for (int i = 0; i < ST_COUNT; ++i)
             if (cudaEventCreate(&s->ev[i]) != cudaSuccess) { rc = fail(CFD_B200_ECUDA, "event create failed"); break; }

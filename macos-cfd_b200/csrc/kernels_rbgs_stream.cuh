@@ -44,7 +44,10 @@
 #define RS_OUT 52   // output columns per warp
 #define RS_HX 6     // halo columns (5 needed; 6 keeps X0 odd = 16-byte aligned pairs in global memory)
 #define RS_HY 5     // halo rows
-#define RS_WARPS 2  // warps per block (independent of each other)
+#ifndef RS_WARPS
+#define RS_WARPS 4  // warps per block (independent of each other; adjacent strips, so a block reads 4 x 512 contiguous bytes per row)
+#endif
+#define RS_BLOCKS_PER_SM (12 / RS_WARPS) // 12 warps per SM fit (shared memory: 17 KB per warp)
 #define RS_ROW 68   // doubles per ring row: 64 columns + 1 pad after every 16
 #define RS_WDOUBLES (2 + RS_R * RS_ROW + 2 + RS_R * RS_ROW) // per warp: pad, p ring, pad, rhs ring
 #define RS_SMEM (RS_WARPS * RS_WDOUBLES * 8)
@@ -69,7 +72,7 @@ struct RsCoarse {
     int P;
 };
 template <int POW2, int VC>
-__global__ void __launch_bounds__(32 * RS_WARPS, 6)
+__global__ void __launch_bounds__(32 * RS_WARPS, RS_BLOCKS_PER_SM)
     k_rbgs_stream(Geom g, const double *__restrict__ pin, double *__restrict__ pout, const double *__restrict__ rhs,
                   Scalars *sc, double *partials, double tol, int RY, int nstrips, int finish, RsCoarse cz) { pdl_begin();
     extern __shared__ double rs_raw[];
