@@ -52,8 +52,8 @@ STAGE_BYTES = {"cfl_dt": 0, "rhs_stage1": 32, "rhs_stage2": 48, "divergence": 24
 SURVEY_STEP_BYTES = {"mg": lambda vcycles, iters: 184 + 64 * vcycles, "pcg": lambda vcycles, iters: 184 + 32 + 80 * iters}
 STAGE_KERNEL = {"rhs_stage1": "k_rhs_march<1>", "rhs_stage2": "k_rhs_march<2>", "divergence": "k_divergence<1>",
                 "project": "k_project", "divergence_post": "k_divergence<0>"}
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/r01_*), 8192 x 8192 only
-NCU_TRAFFIC_8192 = {"k_rbgs_fused": 1.0816e9 + 0.5221e9, "k_rbgs_stream": 1.1258e9 + 0.5112e9, "k_rhs_march<1>": 1.1385e9 + 1.0216e9,
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/r01_*, r01d_* for k_rbgs_stream), 8192 x 8192 only
+NCU_TRAFFIC_8192 = {"k_rbgs_fused": 1.0816e9 + 0.5221e9, "k_rbgs_stream": 1.1235e9 + 0.5104e9, "k_rhs_march<1>": 1.1385e9 + 1.0216e9,
                     "k_rhs_march<2>": 2.1998e9 + 1.0244e9, "k_project": 1.6301e9 + 1.0227e9,
                     "k_divergence<1>": 1.0831e9 + 0.5114e9, "k_divergence<0>": 1.0832e9 + 0.5101e9,
                     "k_pcg_phase1_march + k_pcg_phase2_march (one iteration)": 1.112e9 + 0.510e9 + 1.629e9 + 1.022e9}
