@@ -13,9 +13,11 @@
 //     taken in row L-9.  With two rows between consecutive passes the four updates of a step touch disjoint rows and
 //     are independent of each other (the rows a pass writes, L-1, L-3, L-5, L-7, are never read by another pass in the
 //     same step), so a lane has 4 update chains + 2 residual chains in flight;
-//   * of the four neighbours of an update only two are read from shared memory: the point above this step's point is
-//     next step's horizontal neighbour inside the lane's own column pair, and this step's in-pair neighbour is next
-//     step's point below -- both stay in registers; the residual's own columns are pass 3's last three results;
+//   * of the four neighbours of an update only ONE is read from shared memory (the point above): the point above this
+//     step's point is next step's horizontal neighbour inside the lane's own column pair, this step's in-pair neighbour
+//     is next step's point below -- both stay in registers -- and the neighbour in the adjacent lane's pair is that
+//     lane's in-pair neighbour, fetched with a register shuffle; the residual's own columns are pass 3's last three
+//     results and its cross-lane neighbours the adjacent lanes' copies of those;
 //   * a ring row holds its 64 columns in order with one double of padding after every 16: a lane's column (stride 16 B
 //     across the warp) then hits 16 different bank pairs per half-warp, so every access is conflict-free, and the
 //     cp.async copies read whole sectors of global memory;
@@ -117,16 +119,12 @@ __global__ void __launch_bounds__(32 * RS_WARPS, RS_BLOCKS_PER_SM)
             // ring column i lives at i + (i >> 4)
             const int cpA = lane + (lane >> 4), cpB = 32 + lane + 2 + (lane >> 4); // cp.async destinations
             const int lb = 2 * lane + (lane >> 3);                                  // column a
-            // columns a - 1 and a + 2; lanes 0 / 31 have no such neighbour in the strip (their results are halo garbage
-            // anyway) and read a word of their own whose bank nobody else in the half-warp uses
-            const int lbL = lane == 0 ? 0 : 2 * lane - 1 + ((2 * lane - 1) >> 4);
-            const int lbR = lane == 31 ? 66 : 2 * lane + 2 + ((2 * lane + 2) >> 4);
             // x = colour ^ row parity.  Column offset of the updated point in its pair: E[x] = x ^ par0.
             const int E0 = par0, E1 = par0 ^ 1;
             double *const Bo[2] = {ringp + lb + E0, ringp + lb + E1};               // the updated point
-            const double *const Bh[2] = {ringp + (E0 ? lbR : lbL), ringp + (E1 ? lbR : lbL)}; // its neighbour in the adjacent lane's pair
             const double *const Ro[2] = {ringr + lb + E0, ringr + lb + E1};
             const bool colok[2] = {E0 ? c1 : c0, E1 ? c1 : c0};
+            const int hd[2] = {2 * E0 - 1, 2 * E1 - 1}; // lane offset of that neighbour: column a - 1 or a + 2
             // VC: the wall term of mg_wall(), column part, for the point with column offset E[x]
             const double wxv[2] = {(double)((a + E0 == 1) + (a + E0 == g.nx)) * idx2, (double)((a + E1 == 1) + (a + E1 == g.nx)) * idx2};
             const double wxc[2] = {(double)((a == 1) + (a == g.nx)) * idx2, (double)((a + 1 == 1) + (a + 1 == g.nx)) * idx2}; // by column
@@ -177,7 +175,9 @@ __global__ void __launch_bounds__(32 * RS_WARPS, RS_BLOCKS_PER_SM)
                             bo[k] = Bo[x][((S - 1) & (RS_R - 1)) * RS_ROW];        // this column, the row below
                         }
                         const double pt = Bo[x][((S + 1) & (RS_R - 1)) * RS_ROW]; // this column, the row above
-                        const double ph = Bh[x][S * RS_ROW];          // the horizontal neighbour in the adjacent lane's pair
+                        // the horizontal neighbour in the adjacent lane's pair is that lane's in-pair neighbour ho[k]
+                        // (same pass, same row): a register shuffle instead of a (bank-conflicting) shared-memory load
+                        const double ph = __shfl_sync(0xffffffffu, ho[k], lane + hd[x]);
                         const double rv = Ro[x][S * RS_ROW];
                         const double sum = (ph + ho[k]) * idx2 + (pt + bo[k]) * idy2;
                         double xv;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(32 * RS_WARPS, RS_BLOCKS_PER_SM)
                     if (VC && finish != RS_VC_SMOOTH && (!FILL || rr >= rr_first) && rr <= rr_last) {
                         // kernels_vcycle.cuh, mg_resid: rhs - (L p - wall p), then k_mg_restrict / k_mg_residual_norm
                         const int SR = (u - 9) & (RS_R - 1), jj = ys + rr;
-                        const double hl = ringp[SR * RS_ROW + lbL], hr = ringp[SR * RS_ROW + lbR];
+                        const double hl = __shfl_sync(0xffffffffu, r2[1], lane - 1), hr = __shfl_sync(0xffffffffu, r2[0], lane + 1);
                         const double rhA = ringr[SR * RS_ROW + lb], rhB = ringr[SR * RS_ROW + lb + 1];
                         const double wy = (double)((jj == 1) + (jj == g.ny)) * idy2;
                         double ApA = (r2[1] - 2.0 * r2[0] + hl) * idx2 + (r1[0] - 2.0 * r2[0] + r3[0]) * idy2;
@@ -235,8 +235,8 @@ __global__ void __launch_bounds__(32 * RS_WARPS, RS_BLOCKS_PER_SM)
                     }
                     if (!VC && (!FILL || rr >= rr_first) && rr <= rr_last) {
                         const int SR = (u - 9) & (RS_R - 1);
-                        const double hl = ringp[SR * RS_ROW + lbL];    // column a - 1
-                        const double hr = ringp[SR * RS_ROW + lbR];    // column a + 2
+                        const double hl = __shfl_sync(0xffffffffu, r2[1], lane - 1); // column a - 1: the lane below's pair
+                        const double hr = __shfl_sync(0xffffffffu, r2[0], lane + 1); // column a + 2
                         const double rhA = ringr[SR * RS_ROW + lb], rhB = ringr[SR * RS_ROW + lb + 1];
                         const double ApA = (r2[1] - 2.0 * r2[0] + hl) * idx2 + (r1[0] - 2.0 * r2[0] + r3[0]) * idy2;
                         const double ApB = (hr - 2.0 * r2[1] + r2[0]) * idx2 + (r1[1] - 2.0 * r2[1] + r3[1]) * idy2;

@@ -1,5 +1,5 @@
 cd /root/repo; mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "mg_bit_exact or streaming or full_size" > gpurun_out/pytest_q.log 2>&1; tail -2 gpurun_out/pytest_q.log
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "mg or streaming or full_size or nonfinite or variants" > gpurun_out/pytest_q.log 2>&1; tail -2 gpurun_out/pytest_q.log
 python bench.py --steps 16 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/rs_default.json 2>/dev/null
 python - <<PY
 import json
