@@ -118,6 +118,9 @@ int cfd_b200_comm_mode(const cfd_b200_solver *s);
 /* Tuning / test hook: rows > 0 forces the streaming smoother with `rows` rows per strip on any grid size (the default,
  * 0, picks the strip height from the grid and uses the tile smoother on grids too small to fill the GPU). */
 int cfd_b200_set_smoother_strip(cfd_b200_solver *s, int rows);
+/* Host-only (needs no device): the strip height the streaming smoother would use for a single-GPU nx x ny grid on a GPU
+ * with sm_count SMs (257, 129, 65 or 33 rows), or 0 when the grid is too small for it and the tile smoother runs. */
+int cfd_b200_smoother_strip_for(int nx, int ny, int sm_count);
 /* Which kernel ran the last smooth() of --solver=mg (reference mode): 1 = streaming smoother (large grids), 2 = tile
  * smoother (small grids, and the guarded slow path of 1), 3 = one launch per colour pass (variant 0), 0 = none yet. */
 int cfd_b200_last_smoother(const cfd_b200_solver *s);

@@ -142,6 +142,7 @@ def load_library(build: bool = True):
     L.cfd_b200_render_rgb.argtypes = [S, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p]
     L.cfd_b200_apply_shapes.argtypes = [S, C.POINTER(Shape), C.c_int]
     L.cfd_b200_set_smoother_strip.argtypes = [S, C.c_int]
+    L.cfd_b200_smoother_strip_for.argtypes = [C.c_int, C.c_int, C.c_int]
     L.cfd_b200_destroy.argtypes = [S]
     L.cfd_b200_destroy.restype = None
     L.cfd_b200_upload.argtypes = [S, C.c_void_p, C.c_void_p, C.c_void_p]

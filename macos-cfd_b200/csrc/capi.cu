@@ -522,31 +522,39 @@ void launch_fused(cfd_b200_solver *s, double tol, int ntx, int nty, int finish, 
 
 // Strip height and grid of the streaming smoother for an nx-wide grid with `nrows` stored rows; false when the grid is
 // too small to fill the GPU with it (the caller then uses its tile / per-colour kernels).
-bool stream_plan(const cfd_b200_solver *s, int nx, int nrows, int *RY_out, int *gx_out, int *nstrips_out) {
-    static const int ry_env = getenv("CFD_B200_RB_RY") ? atoi(getenv("CFD_B200_RB_RY")) : 0;
+// Pure host arithmetic (no device needed): strip height for an nx-wide grid with `nrows` stored rows on a GPU with
+// `sm_count` SMs, or 0 when the streaming smoother would leave SMs empty and the tile kernel is the better choice.
+int stream_strip_rows(int nx, int nrows, int sm_count, int *gx_out, int *nstrips_out) {
     const int nstrips = cdiv(nx + 1, RS_OUT), gx = cdiv(nstrips, RS_WARPS);
     // Rows per strip: 16 m + 1, so that the RY + 15 steps of a strip are whole turns of the 16-row ring.  Tall strips
     // waste fewer steps on the pipeline fill, short ones give more blocks.  Cost model fitted on B200 (8192x1024 ...
     // 16384x4096, scripts/strip_sweep.py): a block costs RY + 15 steps + ~12 steps of fixed overhead; the blocks run
-    // in rounds of 6 per SM, a full round at unit cost per step and a partly filled last round at 0.6 + 0.4 x fill
-    // (fewer resident warps hide less latency).  It picks the measured optimum in every case tried: 8192^2 -> 257,
-    // 8192x4096 -> 129, 8192x2048 / 4096^2 -> 257, 8192x1024 -> 129, 2048^2 -> 65.
+    // in rounds of RS_BLOCKS_PER_SM per SM, a full round at unit cost per step and a partly filled last round at
+    // 0.6 + 0.4 x fill (fewer resident warps hide less latency).  It picks the measured optimum in every case tried:
+    // 8192^2 -> 257, 8192x4096 -> 129, 8192x2048 / 4096^2 -> 257, 8192x1024 -> 129, 2048^2 -> 65.
     int RY = 257;
-    {
-        const double slots = (double)RS_BLOCKS_PER_SM * s->sm_count;
-        double best = 1e300;
-        for (int ry = 257; ry >= 33; ry = (ry - 1) / 2 + 1) {
-            const double blocks = (double)gx * cdiv(nrows, ry);
-            const double full = std::floor(blocks / slots), rem = blocks - full * slots;
-            const double cost = (ry + 27) * (full + (rem > 0 ? 0.6 + 0.4 * rem / slots : 0.0));
-            if (cost < best) best = cost, RY = ry;
-        }
+    const double slots = (double)RS_BLOCKS_PER_SM * sm_count;
+    double best = 1e300;
+    for (int ry = 257; ry >= 33; ry = (ry - 1) / 2 + 1) {
+        const double blocks = (double)gx * cdiv(nrows, ry);
+        const double full = std::floor(blocks / slots), rem = blocks - full * slots;
+        const double cost = (ry + 27) * (full + (rem > 0 ? 0.6 + 0.4 * rem / slots : 0.0));
+        if (cost < best) best = cost, RY = ry;
     }
+    if (gx_out) *gx_out = gx;
+    if (nstrips_out) *nstrips_out = nstrips;
+    // too few warps to fill the GPU: the tile kernel is the better one (1024^2: 21 us per smooth against 25)
+    return (long long)gx * cdiv(nrows, RY) * RS_WARPS >= 6LL * sm_count ? RY : 0;
+}
+
+// Strip height and grid of the streaming smoother for this handle; false when the grid is too small to fill the GPU
+// with it (the caller then uses its tile / per-colour kernels).  A forced strip height (tests, tuning) always streams.
+bool stream_plan(const cfd_b200_solver *s, int nx, int nrows, int *RY_out, int *gx_out, int *nstrips_out) {
+    static const int ry_env = getenv("CFD_B200_RB_RY") ? atoi(getenv("CFD_B200_RB_RY")) : 0;
     const int forced = s->rb_strip > 0 ? s->rb_strip : ry_env;
-    if (forced > 0) RY = forced;
-    *RY_out = RY, *gx_out = gx, *nstrips_out = nstrips;
-    // too few blocks to fill the GPU: the tile kernel is the better one (1024^2: 21 us per smooth against 25)
-    return forced > 0 || (long long)gx * cdiv(nrows, RY) * RS_WARPS >= 6LL * s->sm_count;
+    const int ry = stream_strip_rows(nx, nrows, s->sm_count, gx_out, nstrips_out);
+    *RY_out = forced > 0 ? forced : (ry > 0 ? ry : 33);
+    return forced > 0 || ry > 0;
 }
 
 // One smooth() (pressure.cpp:64-111), p -> p_alt.  variant 1: the streaming kernel with the guarded tile kernel behind it
@@ -1188,6 +1196,11 @@ int cfd_b200_set_smoother_strip(cfd_b200_solver *s, int rows) {
     if (!s || rows < 0) return fail(CFD_B200_EINVAL, "bad argument");
     s->rb_strip = rows;
     return 0;
+}
+
+int cfd_b200_smoother_strip_for(int nx, int ny, int sm_count) {
+    if (nx < 4 || ny < 4 || sm_count < 1) return fail(CFD_B200_EINVAL, "bad argument");
+    return stream_strip_rows(nx, ny + 2, sm_count, nullptr, nullptr);
 }
 
 int cfd_b200_last_smoother(const cfd_b200_solver *s) { return s ? s->last_smoother : 0; }
