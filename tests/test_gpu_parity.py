@@ -426,11 +426,87 @@ def test_jet_mg_1024_vs_oracle(cfd):
     compare_run("mg", run_gpu(cfd, *args, strip=257), o, "cfg1, streaming smoother, 257-row strips")
 
 
+class omp_threads:
+    """Thread count of the CPU checkers for the full-size cases (conftest pins OMP_NUM_THREADS=1 before libgomp loads;
+    the mg path is bit-identical across thread counts, PCG differs by ~1e-15 -- SURVEY.md section 8c)."""
+
+    def __init__(self, n=None):
+        import ctypes
+        self.n = n or (os.cpu_count() or 1)
+        self.gomp = ctypes.CDLL("libgomp.so.1")
+
+    def __enter__(self):
+        self.gomp.omp_set_num_threads(self.n)
+
+    def __exit__(self, *a):
+        self.gomp.omp_set_num_threads(1)
+
+
+def oracle_lib():
+    return cfdo.load("ref") if cfdo.have_ref() else cfdo.load("port")
+
+
+@pytest.mark.parametrize("preset", ["lid", "jet"])
+def test_mg_8192_two_steps_vs_oracle_bitwise(cfd, preset):
+    """BASELINE configs[3] / [4] at their named size: 8192^2 fp64, --solver=mg --vcycles=2, two full steps from the
+    preset's initial state, u, v, p and rhs BIT-IDENTICAL to the reference's own sources (oracle/_ref, all host cores;
+    the C port where the prebuilt .so did not travel)."""
+    args = (preset, "mg", 8192, 8192, 1.0, 1.0, 2, 1e-6, 200, 2)
+    with omp_threads():
+        o = run_oracle(oracle_lib(), *args)
+    g = run_gpu(cfd, *args)
+    compare_run("mg", g, o, f"{preset} mg 8192^2")
+
+
+def test_shear_pcg_4096_vs_oracle(cfd, port):
+    """BASELINE configs[2] at its named size: periodic shear, PCG (200 iterations, tol 1e-6), 4096^2 fp64, two steps:
+    rel-L2 <= 1e-10 on u, v, p, iteration counts within +-1 (the port counts iterations; the unmodified reference
+    cannot)."""
+    args = ("shear", "pcg", 4096, 4096, 1.0, 1.0, 2, 1e-6, 200, 2)
+    with omp_threads():
+        o = run_oracle(port, *args)
+    compare_run("pcg", run_gpu(cfd, *args), o, "shear pcg 4096^2")
+
+
+def test_default_grid_pcg_20_steps_vs_recorded_lines(cfd, port):
+    """The reference's own CPU-runnable case (main.cpp:105: 512x256 on 2x1, PCG): 20+ steps against the stdout lines
+    SURVEY.md section 8c recorded from the reference binary (printed with 6-7 significant digits), and field by field
+    against the oracle."""
+    recorded = {  # (preset, tol): {step: (format, dt, divergence_l2, residual)} exactly as printed (main.cpp:152-155)
+        ("lid", 1e-8): {0: ("%.6e", "0.000390625", "2.000060e-02", "5.191889e-01"), 19: ("%.6e", None, "1.231257e-01", "4.603675e+01")},
+        ("jet", 1e-6): {0: ("%g", "3.8147e-06", "4.56377", "1.53529e+06"), 20: ("%g", None, "2.60937", "1.68593e+06")},
+        ("shear", 1e-6): {0: ("%.6e", "0.000390654", "4.730380e-03", "2.371961e+02"), 19: ("%.6e", None, "5.835455e-02", "3.044367e+02")},
+    }
+    for (preset, tol), lines in recorded.items():
+        nx, ny, Lx, Ly, steps = 512, 256, 2.0, 1.0, max(lines) + 1
+        bc, Re, CFL = cfd.preset(preset, Ly)
+        pp = cfd.make_params("pcg", tol=tol, pcg_max_iters=200)
+        s = cfd.Solver(nx, ny, Lx, Ly)
+        if preset == "shear":
+            s.upload(u=cfd.shear_initial_u(nx, ny, Ly))
+        for k in range(steps):
+            info = s.step(bc, Re, CFL, pp)
+            if k in lines:
+                fmt, dt, div, res = lines[k]
+                got_div = s.divergence_l2()  # what the driver prints after the step (main.cpp:151)
+                assert dt is None or "%g" % info.dt == dt, (preset, k, info.dt)
+                assert fmt % got_div == div, (preset, k, got_div, div)
+                assert fmt % info.residual == res, (preset, k, info.residual, res)
+        if preset == "lid":
+            assert "%.7g" % s.max_velocity() == "1.000203"  # "umax 1.000203" of step 19
+        g = dict(zip(("u", "v", "p", "rhs"), s.download()))
+        s.close()
+        with omp_threads():
+            oh, of = run_oracle(port, preset, "pcg", nx, ny, Lx, Ly, steps, tol, 200, 2)
+        for k in ("u", "v", "p"):
+            assert rel_l2(g[k], of[k]) <= PCG_TOL, (preset, k, rel_l2(g[k], of[k]))
+
+
 def test_full_size_properties_8192(cfd):
-    """At BASELINE's full size (8192^2) the oracle is too slow for a field comparison; check properties that do not
-    depend on size: (1) the BC pass is idempotent for non-periodic presets, (2) a projection step leaves s.rhs equal
-    to the divergence of the final (u, v) and divergence_l2 agrees with info.div_after, (3) two identical runs are
-    bit-identical, (4) the top lid row carries the imposed value, (5) the streaming and the tile smoother agree bitwise."""
+    """Size-independent properties at BASELINE's full size (8192^2), next to the field comparison above: (1) the BC pass
+    is idempotent for non-periodic presets, (2) a projection step leaves s.rhs equal to the divergence of the final
+    (u, v) and divergence_l2 agrees with info.div_after, (3) the top lid row carries the imposed value, (4) the
+    streaming and the tile smoother agree bitwise."""
     nx = ny = 8192
     bc, Re, CFL = cfd.preset("lid", 1.0)
     pp = cfd.make_params("mg", vcycles=2)
@@ -449,7 +525,6 @@ def test_full_size_properties_8192(cfd):
     p1 = np.empty((ny + 2, nx + 2))
     s.download(p=p1)
     s.close()
-    # (3) + (5): a second run with the tile smoother (variant 2) instead of the streaming one gives the same bits
     t = cfd.Solver(nx, ny, 1.0, 1.0)
     t.set_variant(2)
     for _ in range(2):
