@@ -3,8 +3,8 @@ cd /root/repo; mkdir -p gpurun_out
 TAG=${1:-r02a}
 timeout 1500 python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/${TAG}_pytest_gpu.log 2>&1; tail -14 gpurun_out/${TAG}_pytest_gpu.log
 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1; tail -2 gpurun_out/${TAG}_smoke.log
-/usr/bin/time -v python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err; tail -c 600 gpurun_out/${TAG}_bench_reference.json; echo; grep -i "non-finite\|Elapsed\|Maximum resident" gpurun_out/${TAG}_bench_reference.err
-/usr/bin/time -v python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_default.json 2> gpurun_out/${TAG}_bench_default.err; grep "Elapsed" gpurun_out/${TAG}_bench_default.err; tail -5 gpurun_out/${TAG}_bench_default.err
+python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err; tail -c 600 gpurun_out/${TAG}_bench_reference.json; echo; grep -ci "non-finite" gpurun_out/${TAG}_bench_reference.err
+python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_default.json 2> gpurun_out/${TAG}_bench_default.err; tail -5 gpurun_out/${TAG}_bench_default.err
 python - <<PY
 import json
 d=json.loads(open('gpurun_out/${TAG}_bench_default.json').read().strip().splitlines()[-1])
