@@ -61,6 +61,7 @@ struct cfd_b200_solver {
     double *u = nullptr, *v = nullptr, *p = nullptr, *rhs = nullptr;
     double *p_alt = nullptr; // ping-pong partner of p for the fused red-black smoother
     double *u1 = nullptr, *v1 = nullptr;           // TimeIntegrator work arrays (time_integrator.hpp:18-19)
+    double *ustar = nullptr, *vstar = nullptr;     // the unprojected velocity of a step (RK stage 2 -> out-of-place projection)
     double *r = nullptr, *sA = nullptr, *sB = nullptr; // PressureSolver work arrays (pressure.hpp:29); z, Ap never stored
     double *scratch_u = nullptr, *scratch_v = nullptr; // stage-level entry points only (lazy)
     double *viz_out = nullptr;                         // nx*ny visualisation scalar (lazy)
@@ -203,7 +204,9 @@ void enqueue_cfl(cfd_b200_solver *s, double Re, double CFL, double dt_override, 
 }
 
 template <int MODE>
-void enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, const double *vin, double *uout, double *vout) {
+void enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, const double *vin, double *uout, double *vout,
+                 const double *uacc = nullptr, const double *vacc = nullptr) {
+    if (!uacc) uacc = uout, vacc = vout; // MODE 2 in place
     const Geom &g = s->g;
     RhsConst k{g.idx, g.idy, g.idx2, g.idy2, invRe};
     const dim3 block(RHS_TX, RHS_TY);
@@ -216,7 +219,7 @@ void enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, const doub
         rc.end[k] = (k ? rc.end[k - 1] : 0) + ntx_ * nty_;
     };
     auto launch_rects = [&]() {
-        if (rc.n > 0) LAUNCH(s, k_rhs_simple<MODE>, rc.end[rc.n - 1], block, g, k, uin, vin, uout, vout, s->d_sc, rc);
+        if (rc.n > 0) LAUNCH(s, k_rhs_simple<MODE>, rc.end[rc.n - 1], block, g, k, uin, vin, uacc, vacc, uout, vout, s->d_sc, rc);
     };
     // Interior faces (all four fluxes MUSCL, for u and v alike): 2 <= ii <= nx-1, 2 <= jj <= ny-1.  The marching kernel
     // takes the part of it that is aligned to the simple kernel's tiles; the tile strips around it (ring included)
@@ -238,7 +241,7 @@ void enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, const doub
     while (RY > 8 && (long long)gxm * cdiv(YB - YA + 1, RY) < (long long)s->sm_count * MARCH_MINBLOCKS) RY /= 2;
     if (ry_env > 0) RY = ry_env;
     dim3 mgrid(gxm, cdiv(YB - YA + 1, RY));
-    LAUNCH(s, k_rhs_march<MODE>, mgrid, 32 * MARCH_WARPS, g, k, uin, vin, uout, vout, s->d_sc, XA, XB, YA, YB, RY);
+    LAUNCH(s, k_rhs_march<MODE>, mgrid, 32 * MARCH_WARPS, g, k, uin, vin, uacc, vacc, uout, vout, s->d_sc, XA, XB, YA, YB, RY);
     add(0, 0, ntx, tyb);                    // bottom strip
     add(0, tyt, ntx, nty - tyt);            // top strip
     add(0, tyb, 1, tyt - tyb);              // left strip
@@ -257,14 +260,15 @@ dim3 row_grid(const cfd_b200_solver *s, int ncols, int nrows, int *rows_per_bloc
     return dim3(gx, cdiv(nrows, rpb));
 }
 
-void enqueue_divergence(cfd_b200_solver *s, int pre, int want_sum, int want_max = 0) {
+void enqueue_divergence(cfd_b200_solver *s, int pre, int want_sum, int want_max = 0, const double *u = nullptr, const double *v = nullptr) {
     const Geom &g = s->g;
+    if (!u) u = s->u, v = s->v;
     int rpb = 4;
     dim3 grid = row_grid(s, g.nx, g.ny, &rpb);
     if (pre)
-        LAUNCH(s, k_divergence<1>, grid, 256, g, s->u, s->v, s->rhs, s->p, s->d_sc, s->partials, want_sum, rpb, 0);
+        LAUNCH(s, k_divergence<1>, grid, 256, g, u, v, s->rhs, s->p, s->d_sc, s->partials, want_sum, rpb, 0);
     else
-        LAUNCH(s, k_divergence<0>, grid, 256, g, s->u, s->v, s->rhs, (double *)nullptr, s->d_sc, s->partials, want_sum, rpb, want_max);
+        LAUNCH(s, k_divergence<0>, grid, 256, g, u, v, s->rhs, (double *)nullptr, s->d_sc, s->partials, want_sum, rpb, want_max);
 }
 
 int pcg_grid(const cfd_b200_solver *s, int ntiles) {
@@ -288,7 +292,7 @@ enum { HALO_UP = 1, HALO_DOWN = 2, HALO_BOTH = 3 }; // direction in which OWNED 
         if (rc_) return rc_;                                                                                    \
     } while (0)
 
-#define NFIELDS 10 // u, v, p, p_alt, rhs, u1, v1, r, sA, sB: arena slots of n doubles each
+#define NFIELDS 12 // u, v, p, p_alt, rhs, u1, v1, r, sA, sB, ustar, vstar: arena slots of n doubles each
 
 // ---- peer-memory bootstrap: exchange CUDA IPC handles over NCCL, map every peer's arena, verify, agree ------------
 struct P2PInfo {
@@ -865,25 +869,41 @@ int enqueue_step(cfd_b200_solver *s, const cfd_b200_bc *bc_in, double Re, double
     enqueue_bc(s, bc, s->u1, s->v1, nullptr, 1); // :106-107
     TRY(halo_exchange2(s, s->u1, s->v1, 2, HALO_BOTH));
     stage_mark(s, ST_RHS2);
-    enqueue_rhs<2>(s, invRe, s->u1, s->v1, s->u, s->v); // :109-147
+    // variant 1: stage 2 leaves the unprojected velocity in ustar / vstar and the projection writes the State's u, v from
+    // them, out of place, together with the divergence of the result (k_project_div); otherwise everything is in place.
+    const bool fused_div = s->variant == 1;
+    double *us = fused_div ? s->ustar : s->u, *vs = fused_div ? s->vstar : s->v;
+    enqueue_rhs<2>(s, invRe, s->u1, s->v1, us, vs, s->u, s->v); // :109-147
     stage_mark(s, ST_BC2);
-    enqueue_bc(s, bc, s->u, s->v, nullptr, 1); // :150-155
-    TRY(halo_exchange2(s, s->v, nullptr, 1, HALO_DOWN)); // divergence of the top cell row reads the v face above it
+    enqueue_bc(s, bc, us, vs, nullptr, 1); // :150-155
+    TRY(halo_exchange2(s, vs, nullptr, 1, HALO_DOWN)); // divergence of the top cell row reads the v face above it
     stage_mark(s, ST_DIV);
-    enqueue_divergence(s, 1, 1); // :158-186
+    enqueue_divergence(s, 1, 1, 0, us, vs); // :158-186
     stage_mark(s, ST_SOLVE);
     s->p_halo_sent = false;
     int rc = enqueue_solve(s, pp, true); // :187
     if (rc) return rc;
     if (!s->p_halo_sent) TRY(halo_exchange2(s, s->p, nullptr, 1, HALO_UP)); // v faces of the bottom row read p one row below the slab
     stage_mark(s, ST_PROJECT);
-    enqueue_project(s, s->d_sc, 0.0, 1, 1); // :188-202 (+ last_residual_ = isfinite(res) ? res : 1e9)
+    // :188-202 (+ last_residual_ = isfinite(res) ? res : 1e9)
+    if (fused_div) {
+        int rpb = 4;
+        const dim3 grid = row_grid(s, cdiv(g.nx + 1, 2), g.ny + 1, &rpb);
+        LAUNCH(s, k_project_div, grid, 256, g, us, vs, s->p, s->u, s->v, s->rhs, s->d_sc, s->partials, rpb);
+    } else {
+        enqueue_project(s, s->d_sc, 0.0, 1, 1);
+    }
     stage_mark(s, ST_BC3);
     enqueue_bc(s, bc, s->u, s->v, s->p, 1); // :205-207
     TRY(halo_exchange2(s, s->u, s->v, 2, HALO_BOTH)); // v row above for the divergence; everything else for the next step
     s->halo_uv_valid = s->nranks > 1;
     stage_mark(s, ST_DIV2);
-    enqueue_divergence(s, 0, 1, 1); // :210-220 (+ max|u|, max|v| for the next step's compute_cfl)
+    if (fused_div) { // :210-220 on the ring (+ its part of max|u|, max|v| for the next step's compute_cfl)
+        const int nfix = (g.bottom ? 2 : 1) * g.nx + 2 * g.ny;
+        LAUNCH(s, k_div_fix, cdiv(nfix, 256), 256, g, s->u, s->v, s->rhs, s->d_sc, s->partials);
+    } else {
+        enqueue_divergence(s, 0, 1, 1);
+    }
     s->cfl_cached = true;
     TRY(reduce_fin(s, RED_STEP_END, 0.0, 0)); // CFL maxima of the next step + the two partial sums of squares
     LAUNCH(s, k_sanitize_if, s->sm_count * 4, 256, g, s->p, s->d_sc); // :236
@@ -1022,7 +1042,7 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
             cudaError_t ea = cudaMalloc(&s->arena, bytes);
             if (ea != cudaSuccess) { rc = fail(ea == cudaErrorMemoryAllocation ? CFD_B200_ENOMEM : CFD_B200_ECUDA, "arena of %zu bytes: %s", bytes, cudaGetErrorString(ea)); break; }
             if (cudaMemsetAsync(s->arena, 0, bytes, s->stream) != cudaSuccess) { rc = fail(CFD_B200_ECUDA, "arena memset failed"); break; }
-            double **fields[NFIELDS] = {&s->u, &s->v, &s->p, &s->p_alt, &s->rhs, &s->u1, &s->v1, &s->r, &s->sA, &s->sB};
+            double **fields[NFIELDS] = {&s->u, &s->v, &s->p, &s->p_alt, &s->rhs, &s->u1, &s->v1, &s->r, &s->sA, &s->sB, &s->ustar, &s->vstar};
             for (int k = 0; k < NFIELDS; ++k) *fields[k] = s->arena + (size_t)k * s->n;
             s->blk[rank] = reinterpret_cast<P2PBlock *>(s->arena + (size_t)NFIELDS * s->n);
         }
@@ -1161,7 +1181,7 @@ int cfd_b200_download_work(cfd_b200_solver *s, double *u1, double *v1) {
 int cfd_b200_reset(cfd_b200_solver *s) {
     if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
     CU(cudaSetDevice(s->device));
-    double *fields[] = {s->u, s->v, s->p, s->p_alt, s->rhs, s->u1, s->v1};
+    double *fields[] = {s->u, s->v, s->p, s->p_alt, s->rhs, s->u1, s->v1, s->ustar, s->vstar};
     for (double *f : fields) CU(cudaMemsetAsync(f, 0, s->n * sizeof(double), s->stream));
     s->cfl_cached = false, s->halo_uv_valid = false;
     return 0;
@@ -1296,7 +1316,7 @@ int cfd_b200_advect(cfd_b200_solver *s, double *du, double *dv) {
     dim3 block(RHS_TX, RHS_TY);
     RhsRects rects{};
     rects.n = 1, rects.ntx[0] = cdiv(g.nx + 1, RHS_TX), rects.end[0] = rects.ntx[0] * cdiv(g.ny + 1, RHS_TY);
-    LAUNCH(s, k_rhs_simple<3>, rects.end[0], block, g, k, s->u, s->v, s->scratch_u, s->scratch_v, s->d_sc, rects);
+    LAUNCH(s, k_rhs_simple<3>, rects.end[0], block, g, k, s->u, s->v, s->scratch_u, s->scratch_v, s->scratch_u, s->scratch_v, s->d_sc, rects);
     if (du && (rc = copy_field(s, s->scratch_u, du, g.nx + 3, g.ny + 2, false))) return rc;
     if (dv && (rc = copy_field(s, s->scratch_v, dv, g.nx + 2, g.ny + 3, false))) return rc;
     CU(cudaStreamSynchronize(s->stream));

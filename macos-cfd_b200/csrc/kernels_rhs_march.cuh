@@ -69,11 +69,12 @@ struct MarchCol { // y-state of one column of one field while marching upwards
 __device__ __forceinline__ double shfl_dn(double x) { return __shfl_down_sync(0xffffffffu, x, 1); }
 __device__ __forceinline__ double shfl_up(double x) { return __shfl_up_sync(0xffffffffu, x, 1); }
 
-// MODE as in k_rhs_simple.  Outputs: ii in [XA, XB], jj in [YA, YB]; each block row-strip covers RY rows.
+// MODE as in k_rhs_simple (uacc / vacc: the accumulator read by MODE 2).  Outputs: ii in [XA, XB], jj in [YA, YB]; each block
+// row-strip covers RY rows.
 template <int MODE>
 __global__ void __launch_bounds__(32 * MARCH_WARPS, MARCH_MINBLOCKS)
-    k_rhs_march(Geom g, RhsConst k, const double *__restrict__ uin, const double *__restrict__ vin, double *uout,
-                double *vout, Scalars *sc, int XA, int XB, int YA, int YB, int RY) { pdl_begin();
+    k_rhs_march(Geom g, RhsConst k, const double *__restrict__ uin, const double *__restrict__ vin, const double *uacc,
+                const double *vacc, double *uout, double *vout, Scalars *sc, int XA, int XB, int YA, int YB, int RY) { pdl_begin();
     const int lane = threadIdx.x & 31;
     const int wx = blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
     const int X0 = XA - 2 + MARCH_COLS * wx; // raw column of lane 0's first column (odd => aligned double2)
@@ -126,9 +127,9 @@ _Pragma(MARCH_STR(unroll MARCH_UNROLL))
         }
         const size_t o = gidx(g, a, jj);
         double2 au = make_double2(0.0, 0.0), av = make_double2(0.0, 0.0);
-        if (MODE == 2 && (st_a || st_b)) { // s.u / s.v, updated in place (only this thread touches these elements)
-            au = *reinterpret_cast<const double2 *>(uout + o);
-            av = *reinterpret_cast<const double2 *>(vout + o);
+        if (MODE == 2 && (st_a || st_b)) { // s.u / s.v (uacc may be uout: only this thread touches these elements)
+            au = *reinterpret_cast<const double2 *>(uacc + o);
+            av = *reinterpret_cast<const double2 *>(vacc + o);
         }
         const double ua = U[0].q0, ub = U[1].q0, va = V[0].q0, vb = V[1].q0; // face velocities of this row
 

@@ -285,8 +285,8 @@ __device__ __forceinline__ double rhs_point(const double *qc, const double *uc, 
 
 // MODE 0: write the sanitised derivatives (stage-level parity entry point cfd_b200_rhs_terms)
 // MODE 1: RK stage 1   out = sanitize(in + dt * sanitize(d))                 (time_integrator.cpp:81-103)
-// MODE 2: RK stage 2   acc = sanitize(0.5 * (acc + in + dt * sanitize(d)))   (time_integrator.cpp:119-147)
-//         (in = u1/v1 is the field the derivative is taken of; acc = s.u/s.v, updated in place)
+// MODE 2: RK stage 2   out = sanitize(0.5 * (acc + in + dt * sanitize(d)))   (time_integrator.cpp:119-147)
+//         (in = u1/v1 is the field the derivative is taken of; acc = s.u/s.v; out may be acc itself or another array)
 // MODE 3: advect_u / advect_v as free functions: the advective derivative only, not sanitised
 #define RHS_TX 32
 #define RHS_TY 8
@@ -298,8 +298,8 @@ struct RhsRects {
 };
 template <int MODE>
 __global__ void __launch_bounds__(RHS_TX *RHS_TY)
-    k_rhs_simple(Geom g, RhsConst k, const double *__restrict__ uin, const double *__restrict__ vin, double *uout,
-                 double *vout, Scalars *sc, RhsRects rc) { pdl_begin();
+    k_rhs_simple(Geom g, RhsConst k, const double *__restrict__ uin, const double *__restrict__ vin, const double *uacc,
+                 const double *vacc, double *uout, double *vout, Scalars *sc, RhsRects rc) { pdl_begin();
     constexpr int S = RHS_TX + 4 + 1; // +1: odd stride
     __shared__ double us[(RHS_TY + 4) * S], vs[(RHS_TY + 4) * S];
     int rk = 0, first = 0;
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(RHS_TX *RHS_TY)
         size_t o = gidx(g, ii, jj);
         if (MODE == 0 || MODE == 3) uout[o] = d;
         if (MODE == 1) uout[o] = sanitize_val(us[c] + dt * d, flag);
-        if (MODE == 2) uout[o] = sanitize_val(0.5 * (uout[o] + us[c] + dt * d), flag);
+        if (MODE == 2) uout[o] = sanitize_val(0.5 * (uacc[o] + us[c] + dt * d), flag);
     }
     if (ii <= g.nx && jj <= JYv) { // v faces: ii in [1, nx], jj in [1, ny+1]
         int ex = (ii == 1) ? -1 : (ii == g.nx) ? 1 : 0;
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(RHS_TX *RHS_TY)
         size_t o = gidx(g, ii, jj);
         if (MODE == 0 || MODE == 3) vout[o] = d;
         if (MODE == 1) vout[o] = sanitize_val(vs[c] + dt * d, flag);
-        if (MODE == 2) vout[o] = sanitize_val(0.5 * (vout[o] + vs[c] + dt * d), flag);
+        if (MODE == 2) vout[o] = sanitize_val(0.5 * (vacc[o] + vs[c] + dt * d), flag);
     }
     if (flag) sc->nonfinite_any = 1;
 }
@@ -475,6 +475,161 @@ __global__ void __launch_bounds__(256)
         pb = pc;
     }
     if (flag) flags->nonfinite_any = 1;
+}
+
+// =========================================================================================================
+// k_project + k_divergence<POST> in ONE pass, OUT OF PLACE (time_integrator.cpp:188-220).  RK stage 2 leaves the
+// unprojected velocity in two scratch fields (us, vs); this kernel reads them and p and writes the State's u, v and --
+// from the same registers -- the divergence of the projected velocity into s.rhs: a thread that has just projected row
+// jj holds its own faces of rows jj-1 and jj, gets the u face right of its pair from the lane above (the last lane of a
+// warp recomputes that one face from us, p: nobody overwrites the inputs) and closes cell row jj-1.  Every block also
+// projects, without storing, the v row above its chunk of rows to close its top cell row.  40 + 24 -> 48 bytes per cell,
+// the final u, v are never re-read.  What the boundary pass behind this kernel changes (time_integrator.cpp:205-207
+// rewrites the ring faces) is redone afterwards by k_div_fix: cell rows 1 / ny and cell columns 1 / nx; on a slab below
+// another one, row ny reads the neighbour's v faces and is left to it as well.  The sum of squares and the CFL maxima
+// (compute_cfl of the next step) are split the same way: interior here, ring there.
+// =========================================================================================================
+__global__ void __launch_bounds__(256)
+    k_project_div(Geom g, const double *__restrict__ us, const double *__restrict__ vs, double *p, double *__restrict__ u,
+                  double *__restrict__ v, double *__restrict__ rhs, Scalars *sc, double *partials, int rpb) { pdl_begin();
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        const double res = sc->res; // last_residual_ = isfinite(res) ? res : 1e9 (pressure.cpp:123, :232)
+        if (!finite_d(res)) {
+            sc->nonfinite_res = 1;
+            sc->res = 1e9;
+        }
+    }
+    const int ii = 1 + 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int lane = threadIdx.x & 31;
+    const bool active = ii <= g.nx + 1;
+    const double dt = sc->dt, idx = g.idx, idy = g.idy;
+    const int jbase = 1 + blockIdx.y * rpb;
+    const int JYv = v_rows(g);
+    const bool pin_t = g.j0 == 0 && ii == 1;     // the thread that holds p(0,0)
+    const bool u_b = ii + 1 <= g.nx + 1, v_a = active && ii <= g.nx, v_b = ii + 1 <= g.nx; // which faces of the pair exist
+    const bool ur_own = lane == 31 && ii + 2 <= g.nx + 1; // this lane recomputes the face right of its pair
+    // cells this kernel closes (the ring: k_div_fix) and faces the boundary pass cannot change (CFL maxima)
+    const bool cA = ii >= 2 && ii <= g.nx - 1, cB = ii + 1 <= g.nx - 1; // cells ii, ii+1 = v faces ii, ii+1
+    const bool fuA = ii >= 2 && ii <= g.nx, fuB = ii + 1 <= g.nx;        // u faces ii, ii+1
+    const int jf_lo = g.bottom ? 2 : 1, ju_hi = g.top ? g.ny - 1 : g.ny, jv_hi = g.ny, jc_hi = g.ny - 1;
+    int flag = 0;
+    double acc[1] = {0.0};
+    double mu = 0.0, mv = 0.0;
+    const size_t P = g.P;
+    size_t o = gidx(g, ii, jbase);
+    const double2 zero2 = make_double2(0.0, 0.0);
+    double2 pb = active ? *reinterpret_cast<const double2 *>(p + o - P) : zero2;
+    if (pin_t && jbase - 1 == 1) pb.x = 0.0;
+    double2 un = zero2, vn = zero2; // projected u, v of the row below
+    double ur = 0.0;                // projected u(ii+2) of the row below
+    const int jlast = min(jbase + rpb, JYv); // jbase + rpb: the row above the chunk (its v faces only, nothing stored)
+#pragma unroll 2
+    for (int jj = jbase; jj <= jlast; ++jj, o += P) {
+        const bool extra = jj == jbase + rpb;
+        const bool urow = !extra && jj <= g.ny;
+        double2 pc = zero2, su = zero2, sv = zero2;
+        double pl = 0.0, pr = 0.0, sur = 0.0;
+        if (active) {
+            pc = *reinterpret_cast<const double2 *>(p + o);
+            if (urow) su = *reinterpret_cast<const double2 *>(us + o);
+            if (v_a) sv = *reinterpret_cast<const double2 *>(vs + o);
+            if (lane == 0 && urow) pl = p[o - 1];
+            if (ur_own && urow) pr = p[o + 2], sur = us[o + 2];
+        }
+        if (pin_t && jj == 1) pc.x = 0.0; // s.p(0,0) = 0 after the solve, time_integrator.cpp:188
+        const double pls = __shfl_up_sync(0xffffffffu, pc.y, 1);
+        if (lane != 0) pl = pls;
+        double2 uu = zero2, vv = zero2;
+        if (urow && active) { // u faces ii, ii+1 of row jj (project.cpp:51-65)
+            uu.x = sanitize_val(su.x - dt * fin0((pc.x - pl) * idx), flag);
+            if (u_b) uu.y = sanitize_val(su.y - dt * fin0((pc.y - pc.x) * idx), flag);
+            if (u_b) *reinterpret_cast<double2 *>(u + o) = uu;
+            else u[o] = uu.x;
+            if (jj >= jf_lo && jj <= ju_hi) {
+                if (fuA) mu = max2(mu, fabs(uu.x));
+                if (fuB) mu = max2(mu, fabs(uu.y));
+            }
+        }
+        double uright = __shfl_down_sync(0xffffffffu, uu.x, 1); // projected u(ii+2, jj)
+        if (ur_own) uright = sanitize_val(sur - dt * fin0((pr - pc.y) * idx), flag); // the same expression, recomputed
+        if (v_a) { // v faces of row jj (project.cpp:69-83); rows up to ny+1 on the top slab
+            vv.x = sanitize_val(sv.x - dt * fin0((pc.x - pb.x) * idy), flag);
+            if (v_b) vv.y = sanitize_val(sv.y - dt * fin0((pc.y - pb.y) * idy), flag);
+            if (!extra) {
+                if (v_b) *reinterpret_cast<double2 *>(v + o) = vv;
+                else v[o] = vv.x;
+                if (jj >= jf_lo && jj <= jv_hi) {
+                    if (cA) mv = max2(mv, fabs(vv.x));
+                    if (cB) mv = max2(mv, fabs(vv.y));
+                }
+            }
+        }
+        if (pin_t && jj == 1) p[o] = 0.0;
+        // divergence of cell row jj-1 (project.cpp:7-42: its per-value guards are identities here, the operands were
+        // sanitised above; the guard on the result stays)
+        const int jc = jj - 1;
+        if (jj > jbase && jc >= jf_lo && jc <= jc_hi) {
+            const double dA = fin0((un.y - un.x) * idx + (vv.x - vn.x) * idy);
+            const double dB = fin0((ur - un.y) * idx + (vv.y - vn.y) * idy);
+            double *pr_ = rhs + o - P;
+            if (cA && cB) {
+                *reinterpret_cast<double2 *>(pr_) = make_double2(dA, dB);
+                acc[0] += dA * dA;
+                acc[0] += dB * dB;
+            } else if (cA) {
+                pr_[0] = dA;
+                acc[0] += dA * dA;
+            } else if (cB) {
+                pr_[1] = dB;
+                acc[0] += dB * dB;
+            }
+        }
+        un = uu, vn = vv, ur = uright;
+        pb = pc;
+    }
+    if (flag) sc->nonfinite_any = 1;
+    block_max_to_global(mu, &sc->umax_bits);
+    block_max_to_global(mv, &sc->vmax_bits);
+    grid_sum<1>(acc, partials, &sc->ticket[0], [=](double(&t)[1]) { sc->div_after = t[0]; }); // k_div_fix finishes
+}
+
+// The cells k_project_div leaves open, after the boundary pass (and, on slabs, after the exchange of the u, v halo rows):
+// cell rows 1 (bottom slab) and ny, then cell columns 1 and nx without the cells of those rows.  Adds its sum of squares
+// to the interior part, finishes div_after (time_integrator.cpp:211-220) and takes the CFL maxima over the faces of its
+// cells.
+__global__ void __launch_bounds__(256)
+    k_div_fix(Geom g, const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ rhs, Scalars *sc,
+              double *partials) { pdl_begin();
+    const int nrow = g.bottom ? 2 : 1, jlo = g.bottom ? 2 : 1, ncolrows = g.ny - jlo; // column cells: rows jlo .. ny-1
+    const int ntot = nrow * g.nx + 2 * ncolrows;
+    double acc[1] = {0.0};
+    double mu = 0.0, mv = 0.0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < ntot; k += gridDim.x * blockDim.x) {
+        int ii, jj;
+        if (k < nrow * g.nx) {
+            const int rr = k / g.nx;
+            ii = 1 + k - rr * g.nx;
+            jj = rr == nrow - 1 ? g.ny : 1;
+        } else {
+            const int c = k - nrow * g.nx;
+            jj = jlo + (c >> 1);
+            ii = (c & 1) ? g.nx : 1;
+        }
+        const size_t o = gidx(g, ii, jj);
+        const double uRr = u[o + 1], uLr = u[o], vTr = v[o + g.P], vBr = v[o];
+        mu = max2(mu, max2(fabs(uLr), fabs(uRr)));
+        mv = max2(mv, max2(fabs(vBr), fabs(vTr)));
+        const double d = fin0((fin0(uRr) - fin0(uLr)) * g.idx + (fin0(vTr) - fin0(vBr)) * g.idy);
+        acc[0] += d * d;
+        rhs[o] = d;
+    }
+    block_max_to_global(mu, &sc->umax_bits);
+    block_max_to_global(mv, &sc->vmax_bits);
+    const double ncell = (double)(g.nx * g.ny_glob);
+    grid_sum<1>(acc, partials, &sc->ticket[0], [=](double(&t)[1]) {
+        const double total = sc->div_after + t[0];
+        sc->div_after = (g.ny == g.ny_glob) ? sqrt(total / ncell) : total; // slabs finish after the allreduce
+    });
 }
 
 // Row slabs, end of a step: one all-gather carries what compute_cfl of the NEXT step and the divergence log need.
