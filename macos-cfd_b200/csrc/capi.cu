@@ -78,6 +78,7 @@ struct cfd_b200_solver {
     int pdl = 3; // programmatic dependent launch between consecutive kernels (bit mask, see cfd_b200_create_slab; CFD_B200_PDL=0 turns it off)
     bool cfl_cached = false;   // umax/vmax of the current device State are already in d_sc (from the last step)
     cfd_b200_bc last_bc{};
+    cfd_b200_bc last_bc_step{}; // BC of the previous step (the p halo rows sent at its end carry that BC's ghost columns)
     int profiling = 0;
     cudaEvent_t ev[ST_COUNT] = {};
     bool ev_valid = false;
@@ -91,7 +92,10 @@ struct cfd_b200_solver {
     P2PBlock *blk[P2P_MAXR] = {};
     unsigned long long halo_epoch = 0, red_epoch = 0;
     double *gathered = nullptr; // 4 doubles per rank (k_slab_pack / k_slab_unpack)
-    bool p_halo_sent = false;   // the solve already delivered the p row the projection reads (rode on its last reduction)
+    bool p_halo_sent = false;   // the solve already delivered the p rows the projection reads (rode on its last reduction)
+    unsigned sent_since_barrier = 0;      // bit fi: a one-way send wrote the neighbours' halo rows of arena field fi since the last reduction
+    unsigned long long ep_uv = 0;         // one-way send that delivers the u, v (and p) halo rows for the next step; 0 = none pending
+    bool p_halo_valid = false;            // the 5 halo rows of p the smoother reads are current (sent at the end of the last step)
     bool halo_uv_valid = false; // the 2 halo rows of u, v are current (set by the exchange that ends a step)
     // V-cycle extension: coarse levels (level 0 aliases p / rhs), allocated on first use
     int mg_nlev = 0;
@@ -179,10 +183,10 @@ void stage_mark(cfd_b200_solver *s, int st) {
 }
 
 // apply_bc_u / apply_bc_v / apply_bc_p in the reference's pass order (left/right, then bottom/top)
-void enqueue_bc(cfd_b200_solver *s, const BcD &bc, double *u, double *v, double *p, int sanitize) {
+void enqueue_bc(cfd_b200_solver *s, const BcD &bc, double *u, double *v, double *p, int sanitize, int halo = 1) {
     const Geom &g = s->g;
     const int nf = p ? 3 : 2; // blockIdx.y = field (u, v, p)
-    LAUNCH(s, k_bc_lr, dim3(cdiv(g.ny + 5, 128), nf), 128, g, bc, u, v, p, sanitize, s->d_sc);
+    LAUNCH(s, k_bc_lr, dim3(cdiv(g.ny + 5, 128), nf), 128, g, bc, u, v, p, sanitize, s->d_sc, halo);
     if (g.bottom || g.top) LAUNCH(s, k_bc_bt, dim3(cdiv(g.nx + 3, 128), nf), 128, g, bc, u, v, p, sanitize, s->d_sc);
 }
 
@@ -435,6 +439,69 @@ int halo_exchange2(cfd_b200_solver *s, double *a, double *b, int rows, int dirs)
     double *f[2] = {a, b};
     return halo_exchange(s, f, b ? 2 : 1, rows, dirs);
 }
+// One-way version of the exchange (p2p.cuh: k_halo_send): my edge rows go into the neighbours' halo rows, nothing waits.
+// fields[k] sends rows[k] rows in direction(s) dirs[k].  *epoch receives what halo_wait / the consumer's edge blocks wait
+// for (0: the rows are already in place in stream order -- single GPU, the NCCL transport, or the handshake fallback).
+// Without the handshake a send is only safe if the neighbours have stopped reading the rows it overwrites: true when a
+// reduction (a barrier) has passed since the last send into the same field; otherwise the old exchange is used.
+int halo_send(cfd_b200_solver *s, double *const *fields, const int *rows, const int *dirs, int nfields, unsigned long long *epoch) {
+    *epoch = 0;
+    if (s->nranks == 1) return 0;
+    const Geom &g = s->g;
+    unsigned mask = 0;
+    for (int k = 0; k < nfields; ++k) {
+        const size_t fi = (size_t)(fields[k] - s->arena) / s->n;
+        if (fields[k] < s->arena || fi >= NFIELDS) return fail(CFD_B200_EINVAL, "halo exchange of a field outside the arena");
+        mask |= 1u << fi;
+    }
+    if (!s->p2p_on || (s->sent_since_barrier & mask)) {
+        for (int k = 0; k < nfields; ++k) TRY(halo_exchange(s, &fields[k], 1, rows[k], dirs[k]));
+        return 0;
+    }
+    s->sent_since_barrier |= mask;
+    SendArgs a{};
+    a.epoch = ++s->halo_epoch;
+    const int lower = g.bottom ? -1 : s->rank - 1, upper = g.top ? -1 : s->rank + 1;
+    int anydir = 0;
+    for (int k = 0; k < nfields; ++k) {
+        double *f = fields[k];
+        const size_t fi = (size_t)(f - s->arena) / s->n;
+        const unsigned long long cnt = (unsigned long long)rows[k] * g.P;
+        auto rowptr = [&](int jj) { return f + (size_t)(jj + CFD_YOFF) * g.P; };
+        auto peer_row = [&](int r, int jj) { return static_cast<double *>(s->peer_arena[r]) + fi * s->peer_n[r] + (size_t)(jj + CFD_YOFF) * g.P; };
+        if (upper >= 0 && (dirs[k] & HALO_UP)) a.job[a.njobs++] = SendJob{rowptr(g.ny - rows[k] + 1), peer_row(upper, 1 - rows[k]), cnt};
+        if (lower >= 0 && (dirs[k] & HALO_DOWN)) a.job[a.njobs++] = SendJob{rowptr(1), peer_row(lower, s->peer_ny[lower] + 1), cnt};
+        anydir |= dirs[k];
+    }
+    if (upper >= 0 && (anydir & HALO_UP)) a.peer_data[1] = &s->blk[upper]->data_flag[0];
+    if (lower >= 0 && (anydir & HALO_DOWN)) a.peer_data[0] = &s->blk[lower]->data_flag[1];
+    unsigned long long total = 0;
+    for (int j = 0; j < a.njobs; ++j) total += a.job[j].count;
+    int grid = (int)((total / 2 + 2047) / 2048);
+    grid = grid < 1 ? 1 : (grid > 64 ? 64 : grid);
+    LAUNCH(s, k_halo_send, grid, 256, a, s->blk[s->rank]);
+    *epoch = a.epoch | ((unsigned long long)anydir << 62); // the directions travel with the epoch (epochs stay far below 2^62)
+    return 0;
+}
+WaitArgs wait_args(const cfd_b200_solver *s, unsigned long long epoch) {
+    WaitArgs w{};
+    const int dirs = (int)(epoch >> 62);
+    w.epoch = epoch & ((1ull << 62) - 1);
+    if (!s->g.bottom && (dirs & HALO_UP)) w.f[0] = &s->blk[s->rank]->data_flag[0];  // rows sent UP by the slab below
+    if (!s->g.top && (dirs & HALO_DOWN)) w.f[1] = &s->blk[s->rank]->data_flag[1];   // rows sent DOWN by the slab above
+    return w;
+}
+int halo_wait(cfd_b200_solver *s, unsigned long long epoch) {
+    if (!epoch) return 0;
+    const WaitArgs w = wait_args(s, epoch);
+    if (w.f[0] || w.f[1]) LAUNCH(s, k_halo_wait, 1, 32, w, s->d_sc);
+    return 0;
+}
+int halo_send2(cfd_b200_solver *s, double *a, double *b, int rows, int dirs, unsigned long long *epoch) {
+    double *f[2] = {a, b};
+    const int r[2] = {rows, rows}, d[2] = {dirs, dirs};
+    return halo_send(s, f, r, d, b ? 2 : 1, epoch);
+}
 // in-place allreduce of `count` doubles in device memory (NCCL path)
 int allreduce(cfd_b200_solver *s, void *dev, int count, ncclRedOp_t op) {
     if (s->nranks == 1) return 0;
@@ -447,6 +514,7 @@ int allreduce(cfd_b200_solver *s, void *dev, int count, ncclRedOp_t op) {
 // in the same kernel on the peer-memory path, as a separate exchange on the NCCL path.
 int reduce_fin(cfd_b200_solver *s, int kind, double tol, int max_iters, double *halo, int rows, int dirs) {
     if (s->nranks == 1) return 0;
+    s->sent_since_barrier = 0; // every rank has left the kernels in front of this point once it has passed it
     if (s->p2p_on) {
         RedArgs a{};
         for (int r = 0; r < s->nranks; ++r) a.blk[r] = s->blk[r];
@@ -803,13 +871,25 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp, bool in_step = 
         if (!in_step) LAUNCH(s, k_solve_begin, 1, 1, s->d_sc);
         if (s->variant != 0) { // fused smooth(): 4 colour passes + residual per launch, p ping-ponged
             for (int vc = 0; vc < pp->vcycles; ++vc) {
-                // 5 rows of p (and, once, of rhs: it is constant during the solve) for the redundant compute
-                if (!single) TRY(halo_exchange2(s, s->p, vc == 0 ? s->rhs : nullptr, RB_HY, HALO_BOTH));
+                // 5 rows of p and, once, of rhs (it is constant during the solve) for the redundant compute.  One-way sends:
+                // the reduction of the previous smooth() (or of the previous step) is the barrier in front of them; the p
+                // rows of the first smooth() of a step usually arrived at the end of the previous step already.
+                if (!single) {
+                    double *f[2];
+                    int n = 0;
+                    if (vc > 0 || !s->p_halo_valid) f[n++] = s->p;
+                    if (vc == 0) f[n++] = s->rhs;
+                    const int rows[2] = {RB_HY, RB_HY}, dirs[2] = {HALO_BOTH, HALO_BOTH};
+                    unsigned long long ep = 0;
+                    if (n) TRY(halo_send(s, f, rows, dirs, n, &ep));
+                    TRY(halo_wait(s, ep));
+                    s->p_halo_valid = false;
+                }
                 enqueue_smooth(s, pp->tol, single);
-                // the residual sum; in a step the last one also carries the row of the new p that the projection of the
-                // slab above reads (time_integrator.cpp:188 follows directly)
+                // the residual sum; in a step the last one also carries the rows of the new p that the projections of the
+                // slabs above and below read (time_integrator.cpp:188 follows directly)
                 const bool carry = in_step && vc == pp->vcycles - 1;
-                if (!single) TRY(reduce_fin(s, RED_RBGS, pp->tol, 0, carry ? s->p_alt : nullptr, 1, HALO_UP));
+                if (!single) TRY(reduce_fin(s, RED_RBGS, pp->tol, 0, carry ? s->p_alt : nullptr, 1, HALO_BOTH));
                 if (carry) s->p_halo_sent = true;
                 double *t = s->p;
                 s->p = s->p_alt;
@@ -858,16 +938,24 @@ int enqueue_step(cfd_b200_solver *s, const cfd_b200_bc *bc_in, double Re, double
     if (!bc_equal(s->last_bc, *bc_in) || s->variant == 0) s->cfl_cached = false;
     s->last_bc = *bc_in;
     stage_mark(s, ST_BC0);
+    // the advection stencil reads 2 rows beyond the slab: sent by the neighbours at the end of the previous step (the
+    // boundary pass below also works on them: it is row-local and reproduces what the neighbour does to its own rows),
+    // or exchanged here when the State was uploaded since
+    if (s->halo_uv_valid) TRY(halo_wait(s, s->ep_uv));
+    s->ep_uv = 0;
+    if (!bc_equal(s->last_bc_step, *bc_in)) s->p_halo_valid = false;
+    s->last_bc_step = *bc_in;
     enqueue_bc(s, bc, s->u, s->v, s->p, 0); // :51-53
-    // the advection stencil reads 2 rows beyond the slab; they are current unless the State was uploaded since
     if (!s->halo_uv_valid) TRY(halo_exchange2(s, s->u, s->v, 2, HALO_BOTH));
     stage_mark(s, ST_CFL);
     enqueue_cfl(s, Re, CFL, dt_override, 0); // :55-66
     stage_mark(s, ST_RHS1);
     enqueue_rhs<1>(s, invRe, s->u, s->v, s->u1, s->v1); // :71-103
     stage_mark(s, ST_BC1);
-    enqueue_bc(s, bc, s->u1, s->v1, nullptr, 1); // :106-107
-    TRY(halo_exchange2(s, s->u1, s->v1, 2, HALO_BOTH));
+    enqueue_bc(s, bc, s->u1, s->v1, nullptr, 1, 0); // :106-107 (own rows: the halo rows arrive with the pass applied)
+    unsigned long long ep = 0;
+    TRY(halo_send2(s, s->u1, s->v1, 2, HALO_BOTH, &ep));
+    TRY(halo_wait(s, ep));
     stage_mark(s, ST_RHS2);
     // variant 1: stage 2 leaves the unprojected velocity in ustar / vstar and the projection writes the State's u, v from
     // them, out of place, together with the divergence of the result (k_project_div); otherwise everything is in place.
@@ -875,15 +963,21 @@ int enqueue_step(cfd_b200_solver *s, const cfd_b200_bc *bc_in, double Re, double
     double *us = fused_div ? s->ustar : s->u, *vs = fused_div ? s->vstar : s->v;
     enqueue_rhs<2>(s, invRe, s->u1, s->v1, us, vs, s->u, s->v); // :109-147
     stage_mark(s, ST_BC2);
-    enqueue_bc(s, bc, us, vs, nullptr, 1); // :150-155
-    TRY(halo_exchange2(s, vs, nullptr, 1, HALO_DOWN)); // divergence of the top cell row reads the v face above it
+    enqueue_bc(s, bc, us, vs, nullptr, 1, 0); // :150-155
+    TRY(halo_send2(s, vs, nullptr, 1, HALO_DOWN, &ep)); // divergence of the top cell row reads the v face above it
+    TRY(halo_wait(s, ep));
     stage_mark(s, ST_DIV);
     enqueue_divergence(s, 1, 1, 0, us, vs); // :158-186
     stage_mark(s, ST_SOLVE);
     s->p_halo_sent = false;
     int rc = enqueue_solve(s, pp, true); // :187
     if (rc) return rc;
-    if (!s->p_halo_sent) TRY(halo_exchange2(s, s->p, nullptr, 1, HALO_UP)); // v faces of the bottom row read p one row below the slab
+    // v faces of the bottom row read p one row below the slab; the fused projection also projects the v row above the slab
+    // (the neighbour's faces, redundantly) to close its top cell row and needs p one row above it
+    if (!s->p_halo_sent) {
+        TRY(halo_send2(s, s->p, nullptr, 1, fused_div ? HALO_BOTH : HALO_UP, &ep));
+        TRY(halo_wait(s, ep));
+    }
     stage_mark(s, ST_PROJECT);
     // :188-202 (+ last_residual_ = isfinite(res) ? res : 1e9)
     if (fused_div) {
@@ -895,17 +989,24 @@ int enqueue_step(cfd_b200_solver *s, const cfd_b200_bc *bc_in, double Re, double
     }
     stage_mark(s, ST_BC3);
     enqueue_bc(s, bc, s->u, s->v, s->p, 1); // :205-207
-    TRY(halo_exchange2(s, s->u, s->v, 2, HALO_BOTH)); // v row above for the divergence; everything else for the next step
-    s->halo_uv_valid = s->nranks > 1;
+    if (!fused_div) TRY(halo_exchange2(s, s->v, nullptr, 1, HALO_DOWN)); // the v row above the slab for the divergence
     stage_mark(s, ST_DIV2);
     if (fused_div) { // :210-220 on the ring (+ its part of max|u|, max|v| for the next step's compute_cfl)
-        const int nfix = (g.bottom ? 2 : 1) * g.nx + 2 * g.ny;
+        const int nfix = ((g.bottom ? 1 : 0) + (g.top ? 1 : 0)) * g.nx + 2 * g.ny;
         LAUNCH(s, k_div_fix, cdiv(nfix, 256), 256, g, s->u, s->v, s->rhs, s->d_sc, s->partials);
     } else {
         enqueue_divergence(s, 0, 1, 1);
     }
     s->cfl_cached = true;
     TRY(reduce_fin(s, RED_STEP_END, 0.0, 0)); // CFL maxima of the next step + the two partial sums of squares
+    if (s->nranks > 1) { // behind that barrier: the rows the neighbours read in the next step (nobody waits for them here)
+        double *f[3] = {s->u, s->v, s->p};
+        const int rows[3] = {2, 2, RB_HY}, dirs[3] = {HALO_BOTH, HALO_BOTH, HALO_BOTH};
+        const bool with_p = pp->solver == CFD_B200_SOLVER_MG && pp->mg_mode == CFD_B200_MG_REFERENCE && s->variant != 0;
+        TRY(halo_send(s, f, rows, dirs, with_p ? 3 : 2, &s->ep_uv));
+        s->halo_uv_valid = true;
+        s->p_halo_valid = with_p;
+    }
     LAUNCH(s, k_sanitize_if, s->sm_count * 4, 256, g, s->p, s->d_sc); // :236
     stage_mark(s, ST_END);
     s->ev_valid = s->profiling != 0;
@@ -929,6 +1030,14 @@ void fill_info(const cfd_b200_solver *s, cfd_b200_step_info *info) {
         info->div_after = std::sqrt(h.div_after / ncell);
     }
     info->nonfinite = (h.nonfinite_any ? 1 : 0) | (h.nonfinite_res ? 2 : 0);
+}
+
+// The one-way send that ends a step may still be arriving from the neighbours: wait for it before anything outside a step
+// touches or invalidates the halo rows.
+int settle_halos(cfd_b200_solver *s) {
+    if (s->ep_uv) TRY(halo_wait(s, s->ep_uv));
+    s->ep_uv = 0;
+    return 0;
 }
 
 // host (reference layout) <-> device (padded layout) copy of one field
@@ -1108,7 +1217,7 @@ int cfd_b200_slab_rows(const cfd_b200_solver *s, int *row0, int *nrows) {
 void cfd_b200_destroy(cfd_b200_solver *s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->stream) settle_halos(s), cudaStreamSynchronize(s->stream);
     p2p_teardown(s);
     if (s->comm) nccl_api().CommDestroy(s->comm);
     if (s->gathered) cudaFree(s->gathered);
@@ -1136,7 +1245,9 @@ int cfd_b200_upload(cfd_b200_solver *s, const double *u, const double *v, const 
     CU(cudaSetDevice(s->device));
     const Geom &g = s->g;
     int rc = 0;
+    if ((rc = settle_halos(s))) return rc;
     if (u || v) s->cfl_cached = false, s->halo_uv_valid = false;
+    if (p) s->p_halo_valid = false;
     if (u && (rc = copy_field(s, s->u, const_cast<double *>(u), g.nx + 3, g.ny + 2, true))) return rc;
     if (v && (rc = copy_field(s, s->v, const_cast<double *>(v), g.nx + 2, g.ny + 3, true))) return rc;
     if (p && (rc = copy_field(s, s->p, const_cast<double *>(p), g.nx + 2, g.ny + 2, true))) return rc;
@@ -1158,6 +1269,7 @@ int cfd_b200_download(cfd_b200_solver *s, double *u, double *v, double *p, doubl
     CU(cudaSetDevice(s->device));
     const Geom &g = s->g;
     int rc = 0;
+    if ((rc = settle_halos(s))) return rc;
     if (u && (rc = copy_field(s, s->u, u, g.nx + 3, g.ny + 2, false))) return rc;
     if (v && (rc = copy_field(s, s->v, v, g.nx + 2, g.ny + 3, false))) return rc;
     if (p && (rc = copy_field(s, s->p, p, g.nx + 2, g.ny + 2, false))) return rc;
@@ -1181,9 +1293,10 @@ int cfd_b200_download_work(cfd_b200_solver *s, double *u1, double *v1) {
 int cfd_b200_reset(cfd_b200_solver *s) {
     if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
     CU(cudaSetDevice(s->device));
+    TRY(settle_halos(s));
     double *fields[] = {s->u, s->v, s->p, s->p_alt, s->rhs, s->u1, s->v1, s->ustar, s->vstar};
     for (double *f : fields) CU(cudaMemsetAsync(f, 0, s->n * sizeof(double), s->stream));
-    s->cfl_cached = false, s->halo_uv_valid = false;
+    s->cfl_cached = false, s->halo_uv_valid = false, s->p_halo_valid = false;
     return 0;
 }
 
@@ -1241,8 +1354,8 @@ int cfd_b200_divergence_l2(cfd_b200_solver *s, double *out) {
     CU(cudaMemsetAsync(&s->d_sc->diag_max_bits, 0, sizeof(unsigned long long), s->stream));
     dim3 grid(cdiv(g.nx, 256), g.ny < 128 ? g.ny : 128);
     if (s->nranks > 1) { // the top cell row reads the v face owned by the slab above
-        int rc = halo_exchange2(s, s->v, nullptr, 1, HALO_DOWN);
-        if (rc) return rc;
+        TRY(settle_halos(s));
+        TRY(halo_exchange2(s, s->v, nullptr, 1, HALO_DOWN));
     }
     LAUNCH(s, k_diag, grid, 256, g, s->u, s->v, s->d_sc, s->partials);
     {
@@ -1269,7 +1382,8 @@ int cfd_b200_max_velocity(cfd_b200_solver *s, double *out) {
 int cfd_b200_apply_bc(cfd_b200_solver *s, const cfd_b200_bc *bc, int which) {
     if (!s || !bc) return fail(CFD_B200_EINVAL, "NULL argument");
     CU(cudaSetDevice(s->device));
-    s->cfl_cached = false, s->halo_uv_valid = false;
+    TRY(settle_halos(s));
+    s->cfl_cached = false, s->halo_uv_valid = false, s->p_halo_valid = false;
     enqueue_bc(s, to_bcd(bc), (which & 1) ? s->u : nullptr, (which & 2) ? s->v : nullptr, (which & 4) ? s->p : nullptr, 0);
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
@@ -1289,6 +1403,7 @@ int cfd_b200_compute_cfl(cfd_b200_solver *s, double Re, double CFL, double *dt_o
 
 int cfd_b200_rhs_terms(cfd_b200_solver *s, double invRe, double *du, double *dv) {
     if (!s || !du || !dv) return fail(CFD_B200_EINVAL, "NULL argument");
+    if (s->nranks > 1) return fail(CFD_B200_EUNSUPPORTED, "stage-level entry points are single-GPU");
     CU(cudaSetDevice(s->device));
     int rc = need_scratch(s);
     if (rc) return rc;
@@ -1346,6 +1461,10 @@ int cfd_b200_diffuse(cfd_b200_solver *s, int which, double invRe, double *d) {
 int cfd_b200_divergence(cfd_b200_solver *s) {
     if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
     CU(cudaSetDevice(s->device));
+    if (s->nranks > 1) { // the top cell row reads the v face owned by the slab above
+        TRY(settle_halos(s));
+        TRY(halo_exchange2(s, s->v, nullptr, 1, HALO_DOWN));
+    }
     enqueue_divergence(s, 0, 0);
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
@@ -1355,8 +1474,11 @@ int cfd_b200_divergence(cfd_b200_solver *s) {
 int cfd_b200_pressure_solve(cfd_b200_solver *s, const cfd_b200_params *pp, double *residual, int *iters) {
     if (!s || !pp) return fail(CFD_B200_EINVAL, "NULL argument");
     CU(cudaSetDevice(s->device));
+    TRY(settle_halos(s));
+    s->p_halo_valid = false;
     int rc = enqueue_solve(s, pp);
     if (rc) return rc;
+    s->p_halo_valid = false;
     CU(cudaMemcpyAsync(s->h_sc, s->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
@@ -1368,6 +1490,7 @@ int cfd_b200_pressure_solve(cfd_b200_solver *s, const cfd_b200_params *pp, doubl
 int cfd_b200_subtract_grad_p(cfd_b200_solver *s, double dt) {
     if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
     CU(cudaSetDevice(s->device));
+    TRY(settle_halos(s));
     s->cfl_cached = false, s->halo_uv_valid = false;
     enqueue_project(s, nullptr, dt, 0);
     CU(cudaStreamSynchronize(s->stream));

@@ -59,18 +59,21 @@ __device__ __forceinline__ void bc_row(double *row, int cR, bool both, int ltype
 // exactly what the neighbour does to its own rows and the halo rows stay current without an exchange.
 // blockIdx.y selects the field (0 = u, 1 = v, 2 = p): one thread per row AND field keeps the chain of dependent global
 // accesses of a thread short -- the pass is pure latency (7.5 us with one thread per row, all three fields, at 1024^2).
-__global__ void k_bc_lr(Geom g, BcD bc, double *u, double *v, double *p, int sanitize, Scalars *sc) { pdl_begin();
-    const int jlo = g.bottom ? 1 : -1;
+// halo = 0: own rows only -- for fields whose halo rows are about to arrive from the neighbours with the pass already
+// applied (a one-way send may land before this kernel runs; working on such a row a second time would, with periodic
+// sides, swap its boundary columns back).
+__global__ void k_bc_lr(Geom g, BcD bc, double *u, double *v, double *p, int sanitize, Scalars *sc, int halo) { pdl_begin();
+    const int jlo = (g.bottom || !halo) ? 1 : -1;
     int jj = blockIdx.x * blockDim.x + threadIdx.x + jlo;
     const int f = blockIdx.y;
     int flag = 0;
     bool both = bc.left.type == BC_PERIODIC && bc.right.type == BC_PERIODIC;
-    if (f == 0 && u && jj <= (g.top ? g.ny : g.ny + 2)) { // apply_bc_u rows, bc.cpp:38-107: u is the normal component here
+    if (f == 0 && u && jj <= ((g.top || !halo) ? g.ny : g.ny + 2)) { // apply_bc_u rows, bc.cpp:38-107: u is the normal component here
         double y = ((g.j0 + jj - 1) + 0.5) * g.dy;
         bc_row(u + gidx(g, 0, jj), g.nx + 1, both, bc.left.type, 0.0, jet_profile(bc, y), bc.right.type, 0.0,
                bc.right.inflow_u, sanitize, flag);
     }
-    if (f == 1 && v && jj <= (g.top ? g.ny + 1 : g.ny + 2)) { // apply_bc_v rows, bc.cpp:192-264: tangential; left Inflow gives 0
+    if (f == 1 && v && jj <= (g.top ? g.ny + 1 : (halo ? g.ny + 2 : g.ny))) { // apply_bc_v rows, bc.cpp:192-264: tangential; left Inflow gives 0
         bc_row(v + gidx(g, 0, jj), g.nx, both, bc.left.type, bc.left.moving, 0.0, bc.right.type,
                bc.right.moving, bc.right.inflow_v, sanitize, flag);
     }
@@ -485,11 +488,19 @@ __global__ void __launch_bounds__(256)
 // warp recomputes that one face from us, p: nobody overwrites the inputs) and closes cell row jj-1.  Every block also
 // projects, without storing, the v row above its chunk of rows to close its top cell row.  40 + 24 -> 48 bytes per cell,
 // the final u, v are never re-read.  What the boundary pass behind this kernel changes (time_integrator.cpp:205-207
-// rewrites the ring faces) is redone afterwards by k_div_fix: cell rows 1 / ny and cell columns 1 / nx; on a slab below
-// another one, row ny reads the neighbour's v faces and is left to it as well.  The sum of squares and the CFL maxima
-// (compute_cfl of the next step) are split the same way: interior here, ring there.
+// rewrites the ring faces) is redone afterwards by k_div_fix: the cell rows at the domain bottom / top and the cell
+// columns 1 / nx.  The sum of squares and the CFL maxima (compute_cfl of the next step) are split the same way:
+// interior here, ring there.
 // =========================================================================================================
-__global__ void __launch_bounds__(256)
+#ifndef PD_MINB
+#define PD_MINB 4
+#endif
+#ifndef PD_UNROLL
+#define PD_UNROLL 2
+#endif
+#define PD_STR2(x) #x
+#define PD_STR(x) PD_STR2(x)
+__global__ void __launch_bounds__(256, PD_MINB)
     k_project_div(Geom g, const double *__restrict__ us, const double *__restrict__ vs, double *p, double *__restrict__ u,
                   double *__restrict__ v, double *__restrict__ rhs, Scalars *sc, double *partials, int rpb) { pdl_begin();
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
@@ -504,14 +515,17 @@ __global__ void __launch_bounds__(256)
     const bool active = ii <= g.nx + 1;
     const double dt = sc->dt, idx = g.idx, idy = g.idy;
     const int jbase = 1 + blockIdx.y * rpb;
-    const int JYv = v_rows(g);
+    // v rows: up to ny+1 on every slab.  Below another slab that row belongs to the neighbour; it is projected here as well
+    // (its vs and p rows were delivered) and stored into the halo row, so that the top cell row closes without waiting
+    // for the neighbour's projection -- the same expression on the same operands, hence the same bits.
+    const int JYv = g.ny + 1;
     const bool pin_t = g.j0 == 0 && ii == 1;     // the thread that holds p(0,0)
     const bool u_b = ii + 1 <= g.nx + 1, v_a = active && ii <= g.nx, v_b = ii + 1 <= g.nx; // which faces of the pair exist
     const bool ur_own = lane == 31 && ii + 2 <= g.nx + 1; // this lane recomputes the face right of its pair
     // cells this kernel closes (the ring: k_div_fix) and faces the boundary pass cannot change (CFL maxima)
     const bool cA = ii >= 2 && ii <= g.nx - 1, cB = ii + 1 <= g.nx - 1; // cells ii, ii+1 = v faces ii, ii+1
     const bool fuA = ii >= 2 && ii <= g.nx, fuB = ii + 1 <= g.nx;        // u faces ii, ii+1
-    const int jf_lo = g.bottom ? 2 : 1, ju_hi = g.top ? g.ny - 1 : g.ny, jv_hi = g.ny, jc_hi = g.ny - 1;
+    const int jf_lo = g.bottom ? 2 : 1, ju_hi = g.top ? g.ny - 1 : g.ny, jv_hi = g.ny, jc_hi = g.top ? g.ny - 1 : g.ny;
     int flag = 0;
     double acc[1] = {0.0};
     double mu = 0.0, mv = 0.0;
@@ -523,7 +537,7 @@ __global__ void __launch_bounds__(256)
     double2 un = zero2, vn = zero2; // projected u, v of the row below
     double ur = 0.0;                // projected u(ii+2) of the row below
     const int jlast = min(jbase + rpb, JYv); // jbase + rpb: the row above the chunk (its v faces only, nothing stored)
-#pragma unroll 2
+_Pragma(PD_STR(unroll PD_UNROLL))
     for (int jj = jbase; jj <= jlast; ++jj, o += P) {
         const bool extra = jj == jbase + rpb;
         const bool urow = !extra && jj <= g.ny;
@@ -593,14 +607,15 @@ __global__ void __launch_bounds__(256)
     grid_sum<1>(acc, partials, &sc->ticket[0], [=](double(&t)[1]) { sc->div_after = t[0]; }); // k_div_fix finishes
 }
 
-// The cells k_project_div leaves open, after the boundary pass (and, on slabs, after the exchange of the u, v halo rows):
-// cell rows 1 (bottom slab) and ny, then cell columns 1 and nx without the cells of those rows.  Adds its sum of squares
+// The cells k_project_div leaves open, after the boundary pass: cell row 1 on the bottom slab, cell row ny on the top slab,
+// then cell columns 1 and nx without the cells of those rows.  Adds its sum of squares
 // to the interior part, finishes div_after (time_integrator.cpp:211-220) and takes the CFL maxima over the faces of its
 // cells.
 __global__ void __launch_bounds__(256)
     k_div_fix(Geom g, const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ rhs, Scalars *sc,
               double *partials) { pdl_begin();
-    const int nrow = g.bottom ? 2 : 1, jlo = g.bottom ? 2 : 1, ncolrows = g.ny - jlo; // column cells: rows jlo .. ny-1
+    const int nrow = (g.bottom ? 1 : 0) + (g.top ? 1 : 0);
+    const int jlo = g.bottom ? 2 : 1, jhi = g.top ? g.ny - 1 : g.ny, ncolrows = jhi - jlo + 1; // column cells: rows jlo .. jhi
     const int ntot = nrow * g.nx + 2 * ncolrows;
     double acc[1] = {0.0};
     double mu = 0.0, mv = 0.0;
@@ -609,7 +624,7 @@ __global__ void __launch_bounds__(256)
         if (k < nrow * g.nx) {
             const int rr = k / g.nx;
             ii = 1 + k - rr * g.nx;
-            jj = rr == nrow - 1 ? g.ny : 1;
+            jj = (rr == 0 && g.bottom) ? 1 : g.ny;
         } else {
             const int c = k - nrow * g.nx;
             jj = jlo + (c >> 1);

@@ -111,6 +111,58 @@ __global__ void __launch_bounds__(256) k_halo_xchg(HaloArgs a, P2PBlock *me, Sca
     if (tid == 0) me->ticket = 0u;
 }
 
+// ---- one-way sends: the exchange above without its two round trips ---------------------------------------------
+// k_halo_send stores my edge rows into the neighbours' halo rows and raises the data flag; it waits for nothing.  The
+// handshake can go because every use of it sits behind a reduction that is a barrier (k_p2p_reduce: a rank that has seen
+// every contribution knows that every rank has finished the kernels in front of its own contribution, i.e. has stopped
+// reading the halo rows of the previous round); capi.cu keeps track of that and falls back to k_halo_xchg otherwise.  The
+// receiver waits where it needs the rows -- k_halo_wait in front of the consumer, or the consumer's own edge blocks
+// (p2p_wait_block), so that the transfer and the neighbour's lateness hide behind the interior work.
+struct SendJob {
+    const double *src;
+    double *dst;
+    unsigned long long count; // doubles (whole rows: a multiple of 16)
+};
+struct SendArgs {
+    SendJob job[8];
+    int njobs;
+    unsigned long long *peer_data[2]; // the neighbours' data flags I raise (NULL: no neighbour there / nothing sent that way)
+    unsigned long long epoch;
+};
+__global__ void __launch_bounds__(256) k_halo_send(SendArgs a, P2PBlock *me) { pdl_begin();
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    for (int j = 0; j < a.njobs; ++j) {
+        const double2 *src = reinterpret_cast<const double2 *>(a.job[j].src);
+        double2 *dst = reinterpret_cast<double2 *>(a.job[j].dst);
+        const size_t n2 = a.job[j].count / 2;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < n2; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&me->ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    if (tid < 2 && a.peer_data[tid]) p2p_signal(a.peer_data[tid], a.epoch); // all rows of all blocks are out
+    if (tid == 0) me->ticket = 0u;
+}
+// Wait until the neighbour(s) have delivered send number `epoch`; f[k] = my own data flag for that side or NULL.
+struct WaitArgs {
+    const unsigned long long *f[2];
+    unsigned long long epoch;
+};
+__global__ void k_halo_wait(WaitArgs w, Scalars *sc) { pdl_begin();
+    if (threadIdx.x < 2 && w.f[threadIdx.x]) p2p_wait(w.f[threadIdx.x], w.epoch, sc);
+}
+// The same wait at the top of a consumer block that reads halo rows (one thread polls, the block follows).
+__device__ __forceinline__ void p2p_wait_block(const WaitArgs &w, int side_mask, Scalars *sc) {
+    if (threadIdx.x + threadIdx.y * blockDim.x == 0) {
+        if ((side_mask & 1) && w.f[0]) p2p_wait(w.f[0], w.epoch, sc);
+        if ((side_mask & 2) && w.f[1]) p2p_wait(w.f[1], w.epoch, sc);
+    }
+    __syncthreads();
+}
+
 // ---- reductions fused with their scalar tails ------------------------------------------------------------------
 enum {
     RED_PCG_INIT = 0, // 2 sums  -> pcg_tail_init

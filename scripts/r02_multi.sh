@@ -3,7 +3,7 @@
 cd /root/repo; mkdir -p gpurun_out
 N=${1:-2}; TAG=${2:-r02a}
 if [ "$3" != "notests" ]; then
-  timeout 1500 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/${TAG}_pytest_multi${N}.log 2>&1; tail -4 gpurun_out/${TAG}_pytest_multi${N}.log
+  timeout 1500 python -m pytest tests/test_gpu_multi.py -m gpu -q > gpurun_out/${TAG}_pytest_multi${N}.log 2>&1; tail -4 gpurun_out/${TAG}_pytest_multi${N}.log
 fi
 ( time timeout 800 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_n${N}.json 2> gpurun_out/${TAG}_bench_n${N}.err ) 2>&1 | grep real; tail -3 gpurun_out/${TAG}_bench_n${N}.err
 python - <<PY

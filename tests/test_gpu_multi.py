@@ -66,7 +66,10 @@ def test_slabs_match_single_gpu(tmp_path, preset, solver, variant, p2p, strip):
     got = run_slabs(n, tmp_path, variant=variant, p2p=p2p, strip=strip, **kw)
     assert str(got["comm_mode"]) == ("p2p" if p2p else "nccl")  # no silent fallback
     hist, (u, v, p, rhs), div_l2, vmax = run_single(kw)
-    assert np.array_equal(got["hist"][:, 0], hist[:, 0])  # dt
+    if solver == "mg":
+        assert np.array_equal(got["hist"][:, 0], hist[:, 0])  # dt
+    else:  # dt = f(max|u|) inherits the last-bit differences of the PCG inner products (as in test_gpu_parity.compare_run)
+        assert np.allclose(got["hist"][:, 0], hist[:, 0], rtol=1e-12, atol=0.0)
     assert abs(float(got["vmax"]) - vmax) <= (0.0 if solver == "mg" else 1e-10 * vmax)
     if solver == "mg":
         for name, a in (("u", u), ("v", v), ("p", p), ("rhs", rhs)):
