@@ -115,6 +115,17 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
  * NVLink (CUDA IPC: halo rows stored straight into the neighbour's arrays, reductions fused with their scalar tails).
  * 2 is chosen when every rank could map every peer; CFD_B200_P2P=0 in the environment forces 1. */
 int cfd_b200_comm_mode(const cfd_b200_solver *s);
+/* Row slabs: every wait for a peer GPU is bounded (CFD_B200_P2P_TIMEOUT_S seconds, default 20).  A slab whose peer does not
+ * arrive in time -- or whose peer reports that one of its own waits ran out -- finishes the step with CFD_B200_ECOMM from
+ * cfd_b200_sync / cfd_b200_step; the State is then invalid on every slab.  cfd_b200_comm_reset (collective: every slab
+ * must call it) clears that condition and restarts the flag protocol; upload or reset the State afterwards. */
+int cfd_b200_comm_reset(cfd_b200_solver *s);
+/* Test hook: keeps this handle's stream busy for `microseconds`, to make one slab late on purpose. */
+int cfd_b200_debug_delay(cfd_b200_solver *s, double microseconds);
+/* Measurement hook: enqueue `reps` slab-communication operations of one kind back to back (0 = reduction fused with its
+ * tail, 1 = one-way send of 2 rows of u, v + wait, 2 = the handshake exchange of the same rows, 3 = reduction with a row of
+ * p riding on it); the caller times them with CUDA events on cfd_b200_stream(). */
+int cfd_b200_debug_comm(cfd_b200_solver *s, int kind, int reps);
 /* Tuning / test hook: rows > 0 forces the streaming smoother with `rows` rows per strip on any grid size (the default,
  * 0, picks the strip height from the grid and uses the tile smoother on grids too small to fill the GPU). */
 int cfd_b200_set_smoother_strip(cfd_b200_solver *s, int rows);

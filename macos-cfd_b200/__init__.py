@@ -142,6 +142,9 @@ def load_library(build: bool = True):
     L.cfd_b200_render_rgb.argtypes = [S, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p]
     L.cfd_b200_apply_shapes.argtypes = [S, C.POINTER(Shape), C.c_int]
     L.cfd_b200_set_smoother_strip.argtypes = [S, C.c_int]
+    L.cfd_b200_comm_reset.argtypes = [S]
+    L.cfd_b200_debug_comm.argtypes = [S, C.c_int, C.c_int]
+    L.cfd_b200_debug_delay.argtypes = [S, C.c_double]
     L.cfd_b200_smoother_strip_for.argtypes = [C.c_int, C.c_int, C.c_int]
     L.cfd_b200_destroy.argtypes = [S]
     L.cfd_b200_destroy.restype = None
@@ -225,6 +228,18 @@ class Solver:
     def comm_mode(self) -> str:
         """How the slabs talk: "single", "nccl" (send/recv + allreduce) or "p2p" (peer memory over NVLink, CUDA IPC)."""
         return ("single", "nccl", "p2p")[self.L.cfd_b200_comm_mode(self.h)]
+
+    def comm_reset(self):
+        """Collective over all slabs: clear a communication failure (CfdError -5) and restart the flag protocol."""
+        self._check(self.L.cfd_b200_comm_reset(self.h))
+
+    def debug_comm(self, kind: int, reps: int):
+        """Measurement hook: enqueue `reps` slab-communication operations (see cfd_b200_debug_comm)."""
+        self._check(self.L.cfd_b200_debug_comm(self.h, kind, reps))
+
+    def debug_delay(self, microseconds: float):
+        """Test hook: keep this slab's stream busy for that long (makes it late; its neighbours run ahead)."""
+        self._check(self.L.cfd_b200_debug_delay(self.h, microseconds))
 
     def set_smoother_strip(self, rows: int):
         """rows > 0: force the streaming smoother with that strip height (tests / tuning); 0: automatic."""

@@ -71,6 +71,11 @@ struct cfd_b200_solver {
     double *partials = nullptr;
     size_t partials_n = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t comm_stream = nullptr; // row slabs: the one-way sends run here, next to the solver's kernels
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool comm_pending = false;          // a send was enqueued on comm_stream since the last join
+    bool defer_rbgs = false;            // the residual sum of the step's last smooth() is completed by the reduction that ends the step
+    double defer_tol = 0.0;
     long long launches = 0;
     int variant = 1;
     int rb_strip = 0;      // > 0: force the streaming smoother with this many rows per strip (tests, tuning)
@@ -91,8 +96,8 @@ struct cfd_b200_solver {
     int peer_ny[P2P_MAXR] = {};
     P2PBlock *blk[P2P_MAXR] = {};
     unsigned long long halo_epoch = 0, red_epoch = 0;
+    unsigned long long p2p_timeout_ns = 20000000000ull;
     double *gathered = nullptr; // 4 doubles per rank (k_slab_pack / k_slab_unpack)
-    bool p_halo_sent = false;   // the solve already delivered the p rows the projection reads (rode on its last reduction)
     unsigned sent_since_barrier = 0;      // bit fi: a one-way send wrote the neighbours' halo rows of arena field fi since the last reduction
     unsigned long long ep_uv = 0;         // one-way send that delivers the u, v (and p) halo rows for the next step; 0 = none pending
     bool p_halo_valid = false;            // the 5 halo rows of p the smoother reads are current (sent at the end of the last step)
@@ -191,6 +196,9 @@ void enqueue_bc(cfd_b200_solver *s, const BcD &bc, double *u, double *v, double 
 }
 
 int reduce_fin(cfd_b200_solver *s, int kind, double tol, int max_iters, double *halo = nullptr, int rows = 0, int dirs = 0);
+WaitArgs wait_args(const cfd_b200_solver *s, unsigned long long epoch);
+int halo_wait(cfd_b200_solver *s, unsigned long long epoch);
+void join_comm(cfd_b200_solver *s);
 
 void enqueue_cfl(cfd_b200_solver *s, double Re, double CFL, double dt_override, int cfl_only) {
     const Geom &g = s->g;
@@ -209,8 +217,9 @@ void enqueue_cfl(cfd_b200_solver *s, double Re, double CFL, double dt_override, 
 
 template <int MODE>
 void enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, const double *vin, double *uout, double *vout,
-                 const double *uacc = nullptr, const double *vacc = nullptr) {
+                 const double *uacc = nullptr, const double *vacc = nullptr, unsigned long long wait_epoch = 0) {
     if (!uacc) uacc = uout, vacc = vout; // MODE 2 in place
+    const WaitArgs hw = wait_args(s, wait_epoch); // row slabs: the blocks that read the neighbours' rows wait for this send
     const Geom &g = s->g;
     RhsConst k{g.idx, g.idy, g.idx2, g.idy2, invRe};
     const dim3 block(RHS_TX, RHS_TY);
@@ -223,7 +232,7 @@ void enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, const doub
         rc.end[k] = (k ? rc.end[k - 1] : 0) + ntx_ * nty_;
     };
     auto launch_rects = [&]() {
-        if (rc.n > 0) LAUNCH(s, k_rhs_simple<MODE>, rc.end[rc.n - 1], block, g, k, uin, vin, uacc, vacc, uout, vout, s->d_sc, rc);
+        if (rc.n > 0) LAUNCH(s, k_rhs_simple<MODE>, rc.end[rc.n - 1], block, g, k, uin, vin, uacc, vacc, uout, vout, s->d_sc, rc, hw);
     };
     // Interior faces (all four fluxes MUSCL, for u and v alike): 2 <= ii <= nx-1, 2 <= jj <= ny-1.  The marching kernel
     // takes the part of it that is aligned to the simple kernel's tiles; the tile strips around it (ring included)
@@ -245,7 +254,7 @@ void enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, const doub
     while (RY > 8 && (long long)gxm * cdiv(YB - YA + 1, RY) < (long long)s->sm_count * MARCH_MINBLOCKS) RY /= 2;
     if (ry_env > 0) RY = ry_env;
     dim3 mgrid(gxm, cdiv(YB - YA + 1, RY));
-    LAUNCH(s, k_rhs_march<MODE>, mgrid, 32 * MARCH_WARPS, g, k, uin, vin, uacc, vacc, uout, vout, s->d_sc, XA, XB, YA, YB, RY);
+    LAUNCH(s, k_rhs_march<MODE>, mgrid, 32 * MARCH_WARPS, g, k, uin, vin, uacc, vacc, uout, vout, s->d_sc, XA, XB, YA, YB, RY, hw);
     add(0, 0, ntx, tyb);                    // bottom strip
     add(0, tyt, ntx, nty - tyt);            // top strip
     add(0, tyb, 1, tyt - tyb);              // left strip
@@ -264,15 +273,17 @@ dim3 row_grid(const cfd_b200_solver *s, int ncols, int nrows, int *rows_per_bloc
     return dim3(gx, cdiv(nrows, rpb));
 }
 
-void enqueue_divergence(cfd_b200_solver *s, int pre, int want_sum, int want_max = 0, const double *u = nullptr, const double *v = nullptr) {
+void enqueue_divergence(cfd_b200_solver *s, int pre, int want_sum, int want_max = 0, const double *u = nullptr, const double *v = nullptr,
+                        unsigned long long wait_epoch = 0) {
     const Geom &g = s->g;
     if (!u) u = s->u, v = s->v;
+    const WaitArgs hw = wait_args(s, wait_epoch);
     int rpb = 4;
     dim3 grid = row_grid(s, g.nx, g.ny, &rpb);
     if (pre)
-        LAUNCH(s, k_divergence<1>, grid, 256, g, u, v, s->rhs, s->p, s->d_sc, s->partials, want_sum, rpb, 0);
+        LAUNCH(s, k_divergence<1>, grid, 256, g, u, v, s->rhs, s->p, s->d_sc, s->partials, want_sum, rpb, 0, hw);
     else
-        LAUNCH(s, k_divergence<0>, grid, 256, g, u, v, s->rhs, (double *)nullptr, s->d_sc, s->partials, want_sum, rpb, want_max);
+        LAUNCH(s, k_divergence<0>, grid, 256, g, u, v, s->rhs, (double *)nullptr, s->d_sc, s->partials, want_sum, rpb, want_max, hw);
 }
 
 int pcg_grid(const cfd_b200_solver *s, int ntiles) {
@@ -415,6 +426,7 @@ int halo_exchange_p2p(cfd_b200_solver *s, double *const *fields, int nfields, in
 // slab below (HALO_DOWN); receive the neighbours' rows into the halo rows.  Rows are contiguous: one message each.
 int halo_exchange(cfd_b200_solver *s, double *const *fields, int nfields, int rows, int dirs) {
     if (s->nranks == 1) return 0;
+    join_comm(s);
     if (s->p2p_on) return halo_exchange_p2p(s, fields, nfields, rows, dirs);
     const Geom &g = s->g;
     NcclApi &n = nccl_api();
@@ -439,6 +451,14 @@ int halo_exchange2(cfd_b200_solver *s, double *a, double *b, int rows, int dirs)
     double *f[2] = {a, b};
     return halo_exchange(s, f, b ? 2 : 1, rows, dirs);
 }
+// The solver's stream waits for everything enqueued on the communication stream so far (free when it has finished).
+void join_comm(cfd_b200_solver *s) {
+    if (!s->comm_pending) return;
+    cudaEventRecord(s->ev_join, s->comm_stream);
+    cudaStreamWaitEvent(s->stream, s->ev_join, 0);
+    s->comm_pending = false;
+}
+
 // One-way version of the exchange (p2p.cuh: k_halo_send): my edge rows go into the neighbours' halo rows, nothing waits.
 // fields[k] sends rows[k] rows in direction(s) dirs[k].  *epoch receives what halo_wait / the consumer's edge blocks wait
 // for (0: the rows are already in place in stream order -- single GPU, the NCCL transport, or the handshake fallback).
@@ -479,7 +499,14 @@ int halo_send(cfd_b200_solver *s, double *const *fields, const int *rows, const 
     for (int j = 0; j < a.njobs; ++j) total += a.job[j].count;
     int grid = (int)((total / 2 + 2047) / 2048);
     grid = grid < 1 ? 1 : (grid > 64 ? 64 : grid);
-    LAUNCH(s, k_halo_send, grid, 256, a, s->blk[s->rank]);
+    // On its own stream, behind everything the solver's stream holds so far: the next kernels do not wait for it (what
+    // they need from the NEIGHBOURS they wait for themselves), so the store, the fence and the flag -- a chain of NVLink
+    // latencies, ~10 us -- overlap with computation.  join_comm() puts the solver's stream behind it again.
+    cudaEventRecord(s->ev_fork, s->stream);
+    cudaStreamWaitEvent(s->comm_stream, s->ev_fork, 0);
+    k_halo_send<<<grid, 256, 0, s->comm_stream>>>(a, s->blk[s->rank], s->d_sc);
+    s->launches++;
+    s->comm_pending = true;
     *epoch = a.epoch | ((unsigned long long)anydir << 62); // the directions travel with the epoch (epochs stay far below 2^62)
     return 0;
 }
@@ -514,11 +541,13 @@ int allreduce(cfd_b200_solver *s, void *dev, int count, ncclRedOp_t op) {
 // in the same kernel on the peer-memory path, as a separate exchange on the NCCL path.
 int reduce_fin(cfd_b200_solver *s, int kind, double tol, int max_iters, double *halo, int rows, int dirs) {
     if (s->nranks == 1) return 0;
+    join_comm(s); // flags are written in epoch order: nothing of the communication stream may still be on its way
     s->sent_since_barrier = 0; // every rank has left the kernels in front of this point once it has passed it
     if (s->p2p_on) {
         RedArgs a{};
         for (int r = 0; r < s->nranks; ++r) a.blk[r] = s->blk[r];
         a.nranks = s->nranks, a.rank = s->rank, a.kind = kind, a.epoch = ++s->red_epoch, a.tol = tol, a.max_iters = max_iters;
+        if (kind == RED_STEP_END && s->defer_rbgs) a.defer_rbgs = 1, a.tol = s->defer_tol, s->defer_rbgs = false;
         if (halo) {
             const Geom &g = s->g;
             const int lower = g.bottom ? -1 : s->rank - 1, upper = g.top ? -1 : s->rank + 1;
@@ -631,7 +660,8 @@ bool stream_plan(const cfd_b200_solver *s, int nx, int nrows, int *RY_out, int *
 
 // One smooth() (pressure.cpp:64-111), p -> p_alt.  variant 1: the streaming kernel with the guarded tile kernel behind it
 // as its slow path (a no-op unless a non-finite value turned up); variant 2: the tile kernel alone.
-void enqueue_smooth(cfd_b200_solver *s, double tol, int finish) {
+void enqueue_smooth(cfd_b200_solver *s, double tol, int finish, unsigned long long wait_epoch = 0) {
+    const WaitArgs hw = wait_args(s, wait_epoch); // row slabs: the neighbours' p / rhs rows this smooth() reads
     const Geom &g = s->g;
     const int ntx = cdiv(g.nx, RB_TX), nty = cdiv(g.ny, RB_TY);
     bool stream = s->variant == 1;
@@ -643,10 +673,11 @@ void enqueue_smooth(cfd_b200_solver *s, double tol, int finish) {
         if (!stream) {
             // too small for the streaming kernel: the tile kernel below runs on its own
         } else if (g.denom_pow2)
-            launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<1, 0>, grid, dim3(32 * RS_WARPS), RS_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, RY, nstrips, finish, RsCoarse{});
+            launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<1, 0>, grid, dim3(32 * RS_WARPS), RS_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, RY, nstrips, finish, RsCoarse{}, hw);
         else
-            launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<0, 0>, grid, dim3(32 * RS_WARPS), RS_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, RY, nstrips, finish, RsCoarse{});
+            launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<0, 0>, grid, dim3(32 * RS_WARPS), RS_SMEM, g, s->p, s->p_alt, s->rhs, s->d_sc, s->partials, tol, RY, nstrips, finish, RsCoarse{}, hw);
     }
+    if (!stream) halo_wait(s, wait_epoch); // the tile kernel has no edge blocks of its own
     if (g.denom_pow2) launch_fused<1>(s, tol, ntx, nty, finish, stream);
     else launch_fused<0>(s, tol, ntx, nty, finish, stream);
     s->last_smoother = stream ? 1 : 2;
@@ -744,9 +775,9 @@ int enqueue_vcycle(cfd_b200_solver *s, const cfd_b200_params *pp, double Lx, dou
             for (int k = n / 2; k > 0; --k) {
                 const int fin = k == 1 ? then : RS_VC_SMOOTH;
                 if (pow2)
-                    launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<1, 1>, grid, dim3(32 * RS_WARPS), RS_SMEM, lg, L.p, L.alt, L.rhs, s->d_sc, s->partials, pp->tol, ry, nstrips, fin, cz);
+                    launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<1, 1>, grid, dim3(32 * RS_WARPS), RS_SMEM, lg, L.p, L.alt, L.rhs, s->d_sc, s->partials, pp->tol, ry, nstrips, fin, cz, WaitArgs{});
                 else
-                    launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<0, 1>, grid, dim3(32 * RS_WARPS), RS_SMEM, lg, L.p, L.alt, L.rhs, s->d_sc, s->partials, pp->tol, ry, nstrips, fin, cz);
+                    launch_kp(s, (s->pdl >> 1) & 1, k_rbgs_stream<0, 1>, grid, dim3(32 * RS_WARPS), RS_SMEM, lg, L.p, L.alt, L.rhs, s->d_sc, s->partials, pp->tol, ry, nstrips, fin, cz, WaitArgs{});
                 double *t = L.p;
                 L.p = L.alt, L.alt = t;
                 if (l == 0) s->p = L.p, s->p_alt = L.alt; // level 0 aliases the State's pressure
@@ -871,6 +902,7 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp, bool in_step = 
         if (!in_step) LAUNCH(s, k_solve_begin, 1, 1, s->d_sc);
         if (s->variant != 0) { // fused smooth(): 4 colour passes + residual per launch, p ping-ponged
             for (int vc = 0; vc < pp->vcycles; ++vc) {
+                unsigned long long ep = 0;
                 // 5 rows of p and, once, of rhs (it is constant during the solve) for the redundant compute.  One-way sends:
                 // the reduction of the previous smooth() (or of the previous step) is the barrier in front of them; the p
                 // rows of the first smooth() of a step usually arrived at the end of the previous step already.
@@ -880,17 +912,14 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp, bool in_step = 
                     if (vc > 0 || !s->p_halo_valid) f[n++] = s->p;
                     if (vc == 0) f[n++] = s->rhs;
                     const int rows[2] = {RB_HY, RB_HY}, dirs[2] = {HALO_BOTH, HALO_BOTH};
-                    unsigned long long ep = 0;
                     if (n) TRY(halo_send(s, f, rows, dirs, n, &ep));
-                    TRY(halo_wait(s, ep));
                     s->p_halo_valid = false;
                 }
-                enqueue_smooth(s, pp->tol, single);
-                // the residual sum; in a step the last one also carries the rows of the new p that the projections of the
-                // slabs above and below read (time_integrator.cpp:188 follows directly)
-                const bool carry = in_step && vc == pp->vcycles - 1;
-                if (!single) TRY(reduce_fin(s, RED_RBGS, pp->tol, 0, carry ? s->p_alt : nullptr, 1, HALO_BOTH));
-                if (carry) s->p_halo_sent = true;
+                enqueue_smooth(s, pp->tol, single, ep); // its edge strips wait for those rows
+                // the residual sum.  Peer-memory transport, inside a step: the last one rides on the reduction that ends the
+                // step (one barrier less: nothing in between depends on it -- the vcycle loop is over either way)
+                if (!single && in_step && s->p2p_on && vc == pp->vcycles - 1) s->defer_rbgs = true, s->defer_tol = pp->tol;
+                else if (!single) TRY(reduce_fin(s, RED_RBGS, pp->tol, 0));
                 double *t = s->p;
                 s->p = s->p_alt;
                 s->p_alt = t;
@@ -937,6 +966,7 @@ int enqueue_step(cfd_b200_solver *s, const cfd_b200_bc *bc_in, double Re, double
     const double invRe = 1.0 / Re; // "1.0 / Re" at time_integrator.cpp:76
     if (!bc_equal(s->last_bc, *bc_in) || s->variant == 0) s->cfl_cached = false;
     s->last_bc = *bc_in;
+    s->defer_rbgs = false;
     stage_mark(s, ST_BC0);
     // the advection stencil reads 2 rows beyond the slab: sent by the neighbours at the end of the previous step (the
     // boundary pass below also works on them: it is row-local and reproduces what the neighbour does to its own rows),
@@ -954,37 +984,33 @@ int enqueue_step(cfd_b200_solver *s, const cfd_b200_bc *bc_in, double Re, double
     stage_mark(s, ST_BC1);
     enqueue_bc(s, bc, s->u1, s->v1, nullptr, 1, 0); // :106-107 (own rows: the halo rows arrive with the pass applied)
     unsigned long long ep = 0;
-    TRY(halo_send2(s, s->u1, s->v1, 2, HALO_BOTH, &ep));
-    TRY(halo_wait(s, ep));
+    TRY(halo_send2(s, s->u1, s->v1, 2, HALO_BOTH, &ep)); // one-way; the edge strips of stage 2 wait for the neighbours' rows
     stage_mark(s, ST_RHS2);
     // variant 1: stage 2 leaves the unprojected velocity in ustar / vstar and the projection writes the State's u, v from
     // them, out of place, together with the divergence of the result (k_project_div); otherwise everything is in place.
     const bool fused_div = s->variant == 1;
     double *us = fused_div ? s->ustar : s->u, *vs = fused_div ? s->vstar : s->v;
-    enqueue_rhs<2>(s, invRe, s->u1, s->v1, us, vs, s->u, s->v); // :109-147
+    enqueue_rhs<2>(s, invRe, s->u1, s->v1, us, vs, s->u, s->v, ep); // :109-147
     stage_mark(s, ST_BC2);
     enqueue_bc(s, bc, us, vs, nullptr, 1, 0); // :150-155
-    TRY(halo_send2(s, vs, nullptr, 1, HALO_DOWN, &ep)); // divergence of the top cell row reads the v face above it
-    TRY(halo_wait(s, ep));
+    TRY(halo_send2(s, vs, nullptr, 1, HALO_DOWN, &ep)); // the divergence of the top cell row reads the v face above it
     stage_mark(s, ST_DIV);
-    enqueue_divergence(s, 1, 1, 0, us, vs); // :158-186
+    enqueue_divergence(s, 1, 1, 0, us, vs, ep); // :158-186; the blocks of the top cell row wait for that row
     stage_mark(s, ST_SOLVE);
-    s->p_halo_sent = false;
     int rc = enqueue_solve(s, pp, true); // :187
     if (rc) return rc;
     // v faces of the bottom row read p one row below the slab; the fused projection also projects the v row above the slab
-    // (the neighbour's faces, redundantly) to close its top cell row and needs p one row above it
-    if (!s->p_halo_sent) {
-        TRY(halo_send2(s, s->p, nullptr, 1, fused_div ? HALO_BOTH : HALO_UP, &ep));
-        TRY(halo_wait(s, ep));
-    }
+    // (the neighbour's faces, redundantly) to close its top cell row and needs p one row above it.  One-way, behind the
+    // solver's last reduction; the chunks of rows at the slab's ends wait for the neighbours' rows.
+    TRY(halo_send2(s, s->p, nullptr, 1, fused_div ? HALO_BOTH : HALO_UP, &ep));
     stage_mark(s, ST_PROJECT);
     // :188-202 (+ last_residual_ = isfinite(res) ? res : 1e9)
     if (fused_div) {
         int rpb = 4;
         const dim3 grid = row_grid(s, cdiv(g.nx + 1, 2), g.ny + 1, &rpb);
-        LAUNCH(s, k_project_div, grid, 256, g, us, vs, s->p, s->u, s->v, s->rhs, s->d_sc, s->partials, rpb);
+        LAUNCH(s, k_project_div, grid, 256, g, us, vs, s->p, s->u, s->v, s->rhs, s->d_sc, s->partials, rpb, wait_args(s, ep));
     } else {
+        TRY(halo_wait(s, ep));
         enqueue_project(s, s->d_sc, 0.0, 1, 1);
     }
     stage_mark(s, ST_BC3);
@@ -1035,6 +1061,7 @@ void fill_info(const cfd_b200_solver *s, cfd_b200_step_info *info) {
 // The one-way send that ends a step may still be arriving from the neighbours: wait for it before anything outside a step
 // touches or invalidates the halo rows.
 int settle_halos(cfd_b200_solver *s) {
+    join_comm(s);
     if (s->ep_uv) TRY(halo_wait(s, s->ep_uv));
     s->ep_uv = 0;
     return 0;
@@ -1145,6 +1172,9 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
     int rc = 0;
     do {
         if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(CFD_B200_ECUDA, "stream create failed"); break; }
+        if (nranks > 1 && (cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+                           cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                           cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess)) { rc = fail(CFD_B200_ECUDA, "communication stream create failed"); break; }
         {   // one arena (a multiple of 2 MiB: its own mapping, one IPC handle): NFIELDS fields + this rank's P2PBlock
             size_t bytes = NFIELDS * s->n * sizeof(double) + sizeof(P2PBlock);
             bytes = (bytes + (2u << 20) - 1) / (2u << 20) * (2u << 20);
@@ -1157,6 +1187,12 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
         }
         if (cudaMalloc(&s->d_sc, sizeof(Scalars)) != cudaSuccess) { rc = fail(CFD_B200_ENOMEM, "scalars alloc failed"); break; }
         cudaMemsetAsync(s->d_sc, 0, sizeof(Scalars), s->stream);
+        {   // bound of every wait for a peer GPU (row slabs): a rank that falls this far behind is reported as CFD_B200_ECOMM
+            const char *e = getenv("CFD_B200_P2P_TIMEOUT_S");
+            const double sec = e && atof(e) > 0.0 ? atof(e) : 20.0;
+            s->p2p_timeout_ns = (unsigned long long)(sec * 1e9);
+            cudaMemcpyAsync(&s->d_sc->p2p_timeout_ns, &s->p2p_timeout_ns, sizeof(unsigned long long), cudaMemcpyHostToDevice, s->stream);
+        }
         if (cudaMallocHost(&s->h_sc, sizeof(Scalars)) != cudaSuccess) { rc = fail(CFD_B200_ENOMEM, "pinned alloc failed"); break; }
         memset(s->h_sc, 0, sizeof(Scalars));
         s->partials_n = 2 * 65536;
@@ -1236,6 +1272,9 @@ void cfd_b200_destroy(cfd_b200_solver *s) {
     if (s->h_sc) cudaFreeHost(s->h_sc);
     for (int i = 0; i < ST_COUNT; ++i)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -1321,7 +1360,74 @@ int cfd_b200_sync(cfd_b200_solver *s, cfd_b200_step_info *info) {
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->stream));
     fill_info(s, info);
-    if (s->h_sc->comm_error) return fail(CFD_B200_ECOMM, "rank %d: a peer did not arrive within %d s (peer-memory exchange)", s->rank, (int)(P2P_TIMEOUT_NS / 1000000000ull));
+    if (s->h_sc->comm_error)
+        return fail(CFD_B200_ECOMM, "rank %d: a peer did not arrive within %.3g s, or reported that itself (peer-memory exchange); cfd_b200_comm_reset re-arms the handles",
+                    s->rank, (double)s->p2p_timeout_ns * 1e-9);
+    return 0;
+}
+
+// Collective over all slabs of a job: forget a communication failure (CFD_B200_ECOMM) and start the flag protocol afresh.
+// Every rank must call it; the State itself is left as it is (upload or reset it: a failed step's fields are invalid).
+int cfd_b200_comm_reset(cfd_b200_solver *s) {
+    if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
+    if (s->nranks == 1) return 0;
+    CU(cudaSetDevice(s->device));
+    NcclApi &nc = nccl_api();
+    if (!bounded_sync(s, 2.0 * (double)s->p2p_timeout_ns * 1e-9 + 10.0)) return fail(CFD_B200_ECOMM, "rank %d: the stream did not drain", s->rank);
+    // nobody may still be storing into my flags when I clear them, nobody may signal before everybody has cleared
+    NCCLCHK(nc.AllReduce(s->gathered, s->gathered, 1, ncclDouble, ncclMin, s->comm, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (s->p2p_on) {
+        P2PBlock *b = s->blk[s->rank];
+        CU(cudaMemsetAsync(b->enter_flag, 0, sizeof(b->enter_flag), s->stream));
+        CU(cudaMemsetAsync(b->data_flag, 0, sizeof(b->data_flag), s->stream));
+        CU(cudaMemsetAsync(b->red_flag, 0, sizeof(b->red_flag), s->stream));
+        CU(cudaMemsetAsync(&b->ticket, 0, sizeof(b->ticket), s->stream));
+    }
+    CU(cudaMemsetAsync(&s->d_sc->comm_error, 0, sizeof(int), s->stream));
+    CU(cudaMemsetAsync(s->d_sc->ticket, 0, sizeof(s->d_sc->ticket), s->stream));
+    s->h_sc->comm_error = 0;
+    s->halo_epoch = s->red_epoch = 0;
+    s->sent_since_barrier = 0, s->ep_uv = 0;
+    s->halo_uv_valid = s->p_halo_valid = s->cfl_cached = false;
+    NCCLCHK(nc.AllReduce(s->gathered, s->gathered, 1, ncclDouble, ncclMin, s->comm, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// Test hook: keeps the handle's stream busy for `microseconds` (one spinning thread), so that a test can make one slab
+// late and let its neighbours run ahead as far as the flag protocol allows.
+int cfd_b200_debug_delay(cfd_b200_solver *s, double microseconds) {
+    if (!s || !(microseconds >= 0.0)) return fail(CFD_B200_EINVAL, "bad argument");
+    CU(cudaSetDevice(s->device));
+    LAUNCH(s, k_debug_delay, 1, 1, (unsigned long long)(microseconds * 1e3));
+    return 0;
+}
+
+// Measurement hook (scripts/comm_probe.py): enqueue `reps` communication operations of one kind back to back.
+//   0 = reduction fused with its tail (k_p2p_reduce / allreduce), 1 = one-way send of 2 rows of u, v + stand-alone wait,
+//   2 = the two-round-trip exchange of the same rows (k_halo_xchg / NCCL send-recv), 3 = reduction with one row of p riding on it
+int cfd_b200_debug_comm(cfd_b200_solver *s, int kind, int reps) {
+    if (!s || reps < 0) return fail(CFD_B200_EINVAL, "bad argument");
+    if (s->nranks == 1) return 0;
+    CU(cudaSetDevice(s->device));
+    TRY(settle_halos(s));
+    for (int i = 0; i < reps; ++i) {
+        unsigned long long ep = 0;
+        switch (kind) {
+        case 0: TRY(reduce_fin(s, RED_DIAG, 0.0, 0)); break;
+        case 1:
+            s->sent_since_barrier = 0; // measurement only: the rows carry no meaning here
+            TRY(halo_send2(s, s->u, s->v, 2, HALO_BOTH, &ep));
+            TRY(halo_wait(s, ep));
+            break;
+        case 2: TRY(halo_exchange2(s, s->u, s->v, 2, HALO_BOTH)); break;
+        case 3: TRY(reduce_fin(s, RED_DIAG, 0.0, 0, s->p, 1, HALO_BOTH)); break;
+        default: return fail(CFD_B200_EINVAL, "bad kind %d", kind);
+        }
+    }
+    s->halo_uv_valid = s->p_halo_valid = false;
+    CU(cudaGetLastError());
     return 0;
 }
 
@@ -1431,7 +1537,7 @@ int cfd_b200_advect(cfd_b200_solver *s, double *du, double *dv) {
     dim3 block(RHS_TX, RHS_TY);
     RhsRects rects{};
     rects.n = 1, rects.ntx[0] = cdiv(g.nx + 1, RHS_TX), rects.end[0] = rects.ntx[0] * cdiv(g.ny + 1, RHS_TY);
-    LAUNCH(s, k_rhs_simple<3>, rects.end[0], block, g, k, s->u, s->v, s->scratch_u, s->scratch_v, s->scratch_u, s->scratch_v, s->d_sc, rects);
+    LAUNCH(s, k_rhs_simple<3>, rects.end[0], block, g, k, s->u, s->v, s->scratch_u, s->scratch_v, s->scratch_u, s->scratch_v, s->d_sc, rects, WaitArgs{});
     if (du && (rc = copy_field(s, s->scratch_u, du, g.nx + 3, g.ny + 2, false))) return rc;
     if (dv && (rc = copy_field(s, s->scratch_v, dv, g.nx + 2, g.ny + 3, false))) return rc;
     CU(cudaStreamSynchronize(s->stream));

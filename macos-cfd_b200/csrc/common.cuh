@@ -73,7 +73,8 @@ struct Scalars {
     unsigned int ticket[4]; // last-block tickets of the grid reductions
     double red[4];          // row slabs: local partial sums handed to the allreduce, then to the k_*_fin kernels
     double viz[4];          // k_viz_scalar: min, max, sum, sum of squares of the visualisation scalar
-    int comm_error;         // a bounded peer wait (p2p.cuh) ran out: the step's results are invalid
+    int comm_error;         // a bounded peer wait ran out, or a peer reported that one of its waits did: results are invalid
+    unsigned long long p2p_timeout_ns; // bound of every peer wait (CFD_B200_P2P_TIMEOUT_S, default 20 s)
     int rb_redo;            // k_rbgs_stream met a non-finite value: the guarded tile kernel redoes this smooth()
 };
 
@@ -192,6 +193,53 @@ __device__ __forceinline__ void block_max_to_global(double m, unsigned long long
             b = other > b ? other : b;
         }
         if (lane == 0 && b != 0ull) atomicMax(dst, b);
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Waiting for a peer GPU (row slabs over NVLink peer memory, p2p.cuh).  Flags are monotonically increasing 64-bit epochs
+// with a single writer.  Every wait is bounded: a peer that never arrives sets Scalars::comm_error instead of hanging
+// the GPU.  A rank in that state writes the POISON epoch wherever it would have signalled, so the failure reaches its
+// peers with the next message (and everybody with the next reduction) instead of leaving them with stale rows.
+// ---------------------------------------------------------------------------------------------------------
+#define P2P_POISON 0xffffffffffffffffull
+__device__ __forceinline__ unsigned long long p2p_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool p2p_wait(const unsigned long long *flag, unsigned long long epoch, Scalars *sc) {
+    const volatile unsigned long long *f = flag;
+    bool ok = true;
+    unsigned long long seen = *f;
+    if (seen < epoch) {
+        const unsigned long long t0 = p2p_now(), limit = sc->p2p_timeout_ns;
+        while ((seen = *f) < epoch) {
+            if (*reinterpret_cast<volatile int *>(&sc->comm_error) || p2p_now() - t0 > limit) {
+                ok = false;
+                break;
+            }
+        }
+    }
+    if (seen == P2P_POISON) ok = false; // the writer of this flag failed
+    if (!ok) sc->comm_error = 1;
+    __threadfence_system();
+    return ok;
+}
+// What a consumer of halo rows waits for: the neighbours' one-way send number `epoch` (p2p.cuh: k_halo_send);
+// f[0] = my data flag for the slab below, f[1] = for the slab above, NULL where nothing is expected.
+struct WaitArgs {
+    const unsigned long long *f[2];
+    unsigned long long epoch;
+};
+// The wait at the top of a consumer block that reads halo rows: one thread polls, the block follows.  Blocks that only
+// read the slab's own rows never call this, so their work overlaps the transfer and the neighbour's lateness.
+__device__ __forceinline__ void p2p_wait_block(const WaitArgs &w, bool below, bool above, Scalars *sc) {
+    if (!(below && w.f[0]) && !(above && w.f[1])) return; // block-uniform
+    if (threadIdx.x + threadIdx.y * blockDim.x == 0) {
+        if (below && w.f[0]) p2p_wait(w.f[0], w.epoch, sc);
+        if (above && w.f[1]) p2p_wait(w.f[1], w.epoch, sc);
     }
     __syncthreads();
 }

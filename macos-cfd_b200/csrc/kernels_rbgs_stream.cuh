@@ -108,7 +108,11 @@ struct RsCoarse {
 template <int POW2, int VC>
 __global__ void __launch_bounds__(32 * RS_WARPS, RS_BLOCKS_PER_SM)
     k_rbgs_stream(Geom g, const double *__restrict__ pin, double *__restrict__ pout, const double *__restrict__ rhs,
-                  Scalars *sc, double *partials, double tol, int RY, int nstrips, int finish, RsCoarse cz) { pdl_begin();
+                  Scalars *sc, double *partials, double tol, int RY, int nstrips, int finish, RsCoarse cz, WaitArgs hw) { pdl_begin();
+    if (!VC) { // row slabs: only the strips at the slab's ends read the neighbours' 5 rows of p and rhs
+        const int yb0 = (g.bottom ? 0 : 1) + blockIdx.y * RY, yb1 = yb0 + RY - 1;
+        p2p_wait_block(hw, yb0 - RS_HY - 1 < 1, yb1 + RS_HY > g.ny, sc);
+    }
     extern __shared__ __align__(16) double rs_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     double *ringp = rs_raw + w * RS_WDOUBLES + 2;   // [slot][RS_ROW]

@@ -74,7 +74,11 @@ __device__ __forceinline__ double shfl_up(double x) { return __shfl_up_sync(0xff
 template <int MODE>
 __global__ void __launch_bounds__(32 * MARCH_WARPS, MARCH_MINBLOCKS)
     k_rhs_march(Geom g, RhsConst k, const double *__restrict__ uin, const double *__restrict__ vin, const double *uacc,
-                const double *vacc, double *uout, double *vout, Scalars *sc, int XA, int XB, int YA, int YB, int RY) { pdl_begin();
+                const double *vacc, double *uout, double *vout, Scalars *sc, int XA, int XB, int YA, int YB, int RY, WaitArgs hw) { pdl_begin();
+    {   // row slabs: only the strips that read the neighbours' rows wait for them (rows y0-2 .. y1+3 are touched)
+        const int yb0 = YA + blockIdx.y * RY, yb1 = min(yb0 + RY - 1, YB);
+        p2p_wait_block(hw, yb0 - 2 < 1, yb1 + 3 > g.ny, sc);
+    }
     const int lane = threadIdx.x & 31;
     const int wx = blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
     const int X0 = XA - 2 + MARCH_COLS * wx; // raw column of lane 0's first column (odd => aligned double2)

@@ -302,13 +302,14 @@ struct RhsRects {
 template <int MODE>
 __global__ void __launch_bounds__(RHS_TX *RHS_TY)
     k_rhs_simple(Geom g, RhsConst k, const double *__restrict__ uin, const double *__restrict__ vin, const double *uacc,
-                 const double *vacc, double *uout, double *vout, Scalars *sc, RhsRects rc) { pdl_begin();
+                 const double *vacc, double *uout, double *vout, Scalars *sc, RhsRects rc, WaitArgs hw) { pdl_begin();
     constexpr int S = RHS_TX + 4 + 1; // +1: odd stride
     __shared__ double us[(RHS_TY + 4) * S], vs[(RHS_TY + 4) * S];
     int rk = 0, first = 0;
     while (rk < rc.n - 1 && (int)blockIdx.x >= rc.end[rk]) first = rc.end[rk], ++rk;
     const int t = blockIdx.x - first, tyr = t / rc.ntx[rk], txr = t - tyr * rc.ntx[rk];
     const int x0 = 1 + (rc.tx0[rk] + txr) * RHS_TX, y0 = 1 + (rc.ty0[rk] + tyr) * RHS_TY;
+    p2p_wait_block(hw, y0 - 2 < 1, y0 + RHS_TY + 1 > g.ny, sc); // row slabs: tiles that read the neighbours' rows
     const int tid = threadIdx.y * RHS_TX + threadIdx.x;
     const int max_col = g.P - CFD_XOFF - 1, max_row = g.rows - CFD_YOFF - 1;
     for (int t = tid; t < (RHS_TY + 4) * (RHS_TX + 4); t += RHS_TX * RHS_TY) {
@@ -360,7 +361,8 @@ __global__ void __launch_bounds__(RHS_TX *RHS_TY)
 template <int PRE>
 __global__ void __launch_bounds__(256)
     k_divergence(Geom g, const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ rhs,
-                 double *p, Scalars *sc, double *partials, int want_sum, int rpb, int want_max) { pdl_begin();
+                 double *p, Scalars *sc, double *partials, int want_sum, int rpb, int want_max, WaitArgs hw) { pdl_begin();
+    p2p_wait_block(hw, false, 1 + (int)(blockIdx.y + 1) * rpb > g.ny, sc); // row slabs: the block of the top cell row reads v(ny+1)
     const int ii = 1 + blockIdx.x * blockDim.x + threadIdx.x;
     double acc[1] = {0.0};
     double mu = 0.0, mv = 0.0; // max |u|, max |v| over all faces (compute_cfl of the NEXT step, metrics.cpp:8-24)
@@ -502,7 +504,9 @@ __global__ void __launch_bounds__(256)
 #define PD_STR(x) PD_STR2(x)
 __global__ void __launch_bounds__(256, PD_MINB)
     k_project_div(Geom g, const double *__restrict__ us, const double *__restrict__ vs, double *p, double *__restrict__ u,
-                  double *__restrict__ v, double *__restrict__ rhs, Scalars *sc, double *partials, int rpb) { pdl_begin();
+                  double *__restrict__ v, double *__restrict__ rhs, Scalars *sc, double *partials, int rpb, WaitArgs hw) { pdl_begin();
+    // row slabs: the chunks at the slab's ends read the neighbours' p row (and the top one the v* row above the slab)
+    p2p_wait_block(hw, blockIdx.y == 0, 1 + (int)(blockIdx.y + 1) * rpb > g.ny, sc);
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
         const double res = sc->res; // last_residual_ = isfinite(res) ? res : 1e9 (pressure.cpp:123, :232)
         if (!finite_d(res)) {

@@ -15,8 +15,9 @@
 //
 // All flags are monotonically increasing 64-bit epochs with a single writer; nothing is ever reset, so there is no
 // ABA window.  The reduce slots are double-buffered on the epoch parity: a rank can be at most one reduce ahead of the
-// slowest one (it needs everybody's contribution to pass the next).  Waits are bounded (P2P_TIMEOUT_NS): a peer that
-// never arrives sets Scalars::comm_error instead of hanging the GPU, and cfd_b200_sync reports CFD_B200_ECOMM.
+// slowest one (it needs everybody's contribution to pass the next).  Waits are bounded (common.cuh: p2p_wait): a peer that
+// never arrives sets Scalars::comm_error instead of hanging the GPU, the failure travels to the peers as a poison epoch,
+// and cfd_b200_sync reports CFD_B200_ECOMM on every rank; cfd_b200_comm_reset re-arms the handles.
 //
 // NCCL (comm.cuh) stays the bootstrap (handle exchange, agreement that every rank mapped its peers) and the fallback
 // when peer mapping is not possible.
@@ -24,7 +25,6 @@
 #include "common.cuh"
 
 #define P2P_MAXR 16
-#define P2P_TIMEOUT_NS 20000000000ull // 20 s
 #define P2P_MAGIC 0xCFDB200000000000ull
 
 struct P2PBlock {
@@ -32,37 +32,16 @@ struct P2PBlock {
     unsigned long long enter_flag[2];       // [0] written by the slab below, [1] by the slab above
     unsigned long long data_flag[2];
     unsigned long long red_flag[2][P2P_MAXR]; // [epoch parity][source rank]
-    double red_val[2][P2P_MAXR][4];
-    unsigned int ticket;
-    unsigned int pad;
+    double red_val[2][P2P_MAXR][6];
+    unsigned int ticket;      // last-block ticket of k_halo_xchg (solver stream)
+    unsigned int send_ticket; // ... of k_halo_send (communication stream; may run next to the kernel above)
 };
 
-__device__ __forceinline__ unsigned long long p2p_now() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-__device__ __forceinline__ void p2p_signal(unsigned long long *flag, unsigned long long epoch) {
+__device__ __forceinline__ void p2p_signal(unsigned long long *flag, unsigned long long epoch, const Scalars *sc) {
     __threadfence_system(); // everything this thread has observed or written is visible before the flag
+    if (*reinterpret_cast<const volatile int *>(&sc->comm_error)) epoch = P2P_POISON; // my data cannot be trusted: say so
     *reinterpret_cast<volatile unsigned long long *>(flag) = epoch;
 }
-__device__ __forceinline__ bool p2p_wait(const unsigned long long *flag, unsigned long long epoch, Scalars *sc) {
-    const volatile unsigned long long *f = flag;
-    bool ok = true;
-    if (*f < epoch) {
-        const unsigned long long t0 = p2p_now();
-        while (*f < epoch) {
-            if (*reinterpret_cast<volatile int *>(&sc->comm_error) || p2p_now() - t0 > P2P_TIMEOUT_NS) {
-                sc->comm_error = 1;
-                ok = false;
-                break;
-            }
-        }
-    }
-    __threadfence_system();
-    return ok;
-}
-
 struct HaloJob {
     const double *src; // my rows
     double *dst;       // the neighbour's halo rows (peer memory)
@@ -81,7 +60,7 @@ __global__ void __launch_bounds__(256) k_halo_xchg(HaloArgs a, P2PBlock *me, Sca
     const int tid = threadIdx.x;
     // 1. handshake: the neighbour may write into my halo rows from now on, and I into its rows once it says the same
     if (tid < 2) {
-        if (blockIdx.x == 0 && a.peer_enter[tid]) p2p_signal(a.peer_enter[tid], a.epoch);
+        if (blockIdx.x == 0 && a.peer_enter[tid]) p2p_signal(a.peer_enter[tid], a.epoch, sc);
         bool ok = true;
         if (a.peer_enter[tid]) ok = p2p_wait(&me->enter_flag[tid], a.epoch, sc);
         if (tid == 0) s_go = 1;
@@ -105,7 +84,7 @@ __global__ void __launch_bounds__(256) k_halo_xchg(HaloArgs a, P2PBlock *me, Sca
     if (!s_last) return;
     // 3. the last block: all rows of all blocks are out -> data flags, then wait for the neighbours' rows
     if (tid < 2 && a.peer_data[tid]) {
-        p2p_signal(a.peer_data[tid], a.epoch);
+        p2p_signal(a.peer_data[tid], a.epoch, sc);
         p2p_wait(&me->data_flag[tid], a.epoch, sc);
     }
     if (tid == 0) me->ticket = 0u;
@@ -129,7 +108,7 @@ struct SendArgs {
     unsigned long long *peer_data[2]; // the neighbours' data flags I raise (NULL: no neighbour there / nothing sent that way)
     unsigned long long epoch;
 };
-__global__ void __launch_bounds__(256) k_halo_send(SendArgs a, P2PBlock *me) { pdl_begin();
+__global__ void __launch_bounds__(256) k_halo_send(SendArgs a, P2PBlock *me, const Scalars *sc) {
     __shared__ int s_last;
     const int tid = threadIdx.x;
     for (int j = 0; j < a.njobs; ++j) {
@@ -140,27 +119,19 @@ __global__ void __launch_bounds__(256) k_halo_send(SendArgs a, P2PBlock *me) { p
     }
     __threadfence_system();
     __syncthreads();
-    if (tid == 0) s_last = atomicAdd(&me->ticket, 1u) == gridDim.x - 1;
+    if (tid == 0) s_last = atomicAdd(&me->send_ticket, 1u) == gridDim.x - 1;
     __syncthreads();
     if (!s_last) return;
-    if (tid < 2 && a.peer_data[tid]) p2p_signal(a.peer_data[tid], a.epoch); // all rows of all blocks are out
-    if (tid == 0) me->ticket = 0u;
+    if (tid < 2 && a.peer_data[tid]) p2p_signal(a.peer_data[tid], a.epoch, sc); // all rows of all blocks are out
+    if (tid == 0) me->send_ticket = 0u;
 }
-// Wait until the neighbour(s) have delivered send number `epoch`; f[k] = my own data flag for that side or NULL.
-struct WaitArgs {
-    const unsigned long long *f[2];
-    unsigned long long epoch;
-};
+// Stand-alone wait for the neighbours' send number `epoch` (consumers that have no edge blocks of their own).
 __global__ void k_halo_wait(WaitArgs w, Scalars *sc) { pdl_begin();
     if (threadIdx.x < 2 && w.f[threadIdx.x]) p2p_wait(w.f[threadIdx.x], w.epoch, sc);
 }
-// The same wait at the top of a consumer block that reads halo rows (one thread polls, the block follows).
-__device__ __forceinline__ void p2p_wait_block(const WaitArgs &w, int side_mask, Scalars *sc) {
-    if (threadIdx.x + threadIdx.y * blockDim.x == 0) {
-        if ((side_mask & 1) && w.f[0]) p2p_wait(w.f[0], w.epoch, sc);
-        if ((side_mask & 2) && w.f[1]) p2p_wait(w.f[1], w.epoch, sc);
-    }
-    __syncthreads();
+__global__ void k_debug_delay(unsigned long long ns) { pdl_begin();
+    const unsigned long long t0 = p2p_now();
+    while (p2p_now() - t0 < ns) {}
 }
 
 // ---- reductions fused with their scalar tails ------------------------------------------------------------------
@@ -169,7 +140,7 @@ enum {
     RED_PCG1,         // 1 sum   -> pcg_tail1
     RED_PCG2,         // 2 sums  -> pcg_tail2
     RED_RBGS,         // 1 sum   -> rbgs_tail
-    RED_STEP_END,     // max|u|, max|v|, sum div^2 before / after (end of a step)
+    RED_STEP_END,     // max|u|, max|v|, sum div^2 before / after (end of a step); + the deferred residual sum of the last smooth()
     RED_CFL,          // max|u|, max|v| (compute_cfl after an upload)
     RED_DIAG          // divergence_l2 sum + max_velocity max
 };
@@ -179,6 +150,7 @@ struct RedArgs {
     unsigned long long epoch;
     double tol;
     int max_iters;
+    int defer_rbgs; // RED_STEP_END also completes the last smooth() of the step (its local sum waits in Scalars::red[0])
     // optional: a halo exchange riding on the reduction (halo = 1).  The reduction is a barrier -- a rank that has seen
     // every contribution knows that every rank has finished the kernels in front of its own contribution, i.e. has
     // stopped reading its halo rows -- so the rows can be stored without the handshake of k_halo_xchg.
@@ -192,10 +164,11 @@ struct RedArgs {
 __global__ void __launch_bounds__(P2P_RED_THREADS) k_p2p_reduce(RedArgs a, Scalars *sc) { pdl_begin();
     const int t = threadIdx.x, par = (int)(a.epoch & 1ull);
     P2PBlock *me = a.blk[a.rank];
-    double v0, v1, v2 = 0.0, v3 = 0.0;
+    double v0, v1, v2 = 0.0, v3 = 0.0, v4 = 0.0;
     switch (a.kind) { // every lane reads the same few words; lanes < nranks forward them
     case RED_STEP_END:
         v2 = sc->div_before, v3 = sc->div_after; // partial sums of squares
+        v4 = sc->red[0];
         // fallthrough
     case RED_CFL:
         v0 = __longlong_as_double((long long)sc->umax_bits), v1 = __longlong_as_double((long long)sc->vmax_bits);
@@ -209,14 +182,14 @@ __global__ void __launch_bounds__(P2P_RED_THREADS) k_p2p_reduce(RedArgs a, Scala
     if (t < a.nranks) {
         P2PBlock *dst = a.blk[t];
         volatile double *slot = dst->red_val[par][a.rank];
-        slot[0] = v0, slot[1] = v1, slot[2] = v2, slot[3] = v3;
-        p2p_signal(&dst->red_flag[par][a.rank], a.epoch);
+        slot[0] = v0, slot[1] = v1, slot[2] = v2, slot[3] = v3, slot[4] = v4;
+        p2p_signal(&dst->red_flag[par][a.rank], a.epoch, sc);
         p2p_wait(&me->red_flag[par][t], a.epoch, sc);
     }
     __syncthreads();
     if (t == 0) {
     const bool is_max0 = a.kind == RED_STEP_END || a.kind == RED_CFL, is_max1 = is_max0 || a.kind == RED_DIAG;
-    double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0, r4 = 0.0;
     for (int r = 0; r < a.nranks; ++r) { // fixed rank order: bit-identical on every rank
         const volatile double *slot = me->red_val[par][r];
         const double x0 = slot[0], x1 = slot[1];
@@ -224,6 +197,7 @@ __global__ void __launch_bounds__(P2P_RED_THREADS) k_p2p_reduce(RedArgs a, Scala
         r1 = is_max1 ? max2(r1, x1) : r1 + x1;
         r2 += slot[2];
         r3 += slot[3];
+        r4 += slot[4];
     }
     switch (a.kind) {
     case RED_PCG_INIT: pcg_tail_init(sc, r0, r1, a.tol, a.max_iters); break;
@@ -232,6 +206,10 @@ __global__ void __launch_bounds__(P2P_RED_THREADS) k_p2p_reduce(RedArgs a, Scala
     case RED_RBGS: if (!sc->done) rbgs_tail(sc, r0, a.tol); break;
     case RED_STEP_END:
         sc->div_before = r2, sc->div_after = r3;
+        if (a.defer_rbgs && !sc->done) { // the last smooth() of the step: no decision of the step depended on its residual
+            rbgs_tail(sc, r4, a.tol);
+            if (!finite_d(sc->res)) sc->nonfinite_res = 1, sc->res = 1e9; // last_residual_ (pressure.cpp:123)
+        }
         // fallthrough
     case RED_CFL:
         sc->umax_bits = (unsigned long long)__double_as_longlong(r0), sc->vmax_bits = (unsigned long long)__double_as_longlong(r1);
@@ -253,7 +231,7 @@ __global__ void __launch_bounds__(P2P_RED_THREADS) k_p2p_reduce(RedArgs a, Scala
     __threadfence_system();
     __syncthreads();
     if (t < 2 && a.peer_data[t]) {
-        p2p_signal(a.peer_data[t], a.hepoch);
+        p2p_signal(a.peer_data[t], a.hepoch, sc);
         p2p_wait(&me->data_flag[t], a.hepoch, sc);
     }
 }

@@ -34,6 +34,9 @@ def main():
     ap.add_argument("--variant", type=int, default=1)
     ap.add_argument("--strip", type=int, default=0)  # > 0: force the streaming smoother with this strip height
     ap.add_argument("--p2p", type=int, default=1)  # 0: force the NCCL path (CFD_B200_P2P=0)
+    ap.add_argument("--delay-rank", type=int, default=-1)  # this rank's stream is kept busy before every step (test hook)
+    ap.add_argument("--delay-us", type=float, default=0.0)
+    ap.add_argument("--reset-after", type=int, default=-1)  # collective cfd_b200_comm_reset after that many steps
     ap.add_argument("--out", required=True)
     a = ap.parse_args()
     os.environ["CFD_B200_P2P"] = str(a.p2p)
@@ -53,7 +56,11 @@ def main():
     if a.preset == "shear":
         s.upload(u=np.ascontiguousarray(cfd.shear_initial_u(a.nx, a.ny, a.Ly)[r0:r0 + n + 2]))
     hist = []
-    for _ in range(a.steps):
+    for k in range(a.steps):
+        if k == a.reset_after:
+            s.comm_reset()
+        if rank == a.delay_rank % world and a.delay_us > 0:
+            s.debug_delay(a.delay_us)  # the neighbours run ahead as far as the flag protocol lets them
         info = s.step(bc, Re, CFL, pp)
         hist.append((info.dt, info.residual, info.iters, info.div_before, info.div_after))
     div_l2, vmax = s.divergence_l2(), s.max_velocity()
