@@ -391,6 +391,8 @@ def run_workload(ctx, name, steps, warmup, variant=1, want_e2e=True, want_parity
     # ---- device-resident timing: K steps, CUDA events on the launching stream
     sampler = ClockSampler(ctx.local_rank)
     sampler.start()
+    if N > 1:
+        s.wait_stats(reset=True)
     l0 = s.launch_count
     ctx.barrier()
     # The reference's `mg` mode diverges: at 8192^2 the pressure residual is non-finite by step ~6-8.
@@ -450,6 +452,8 @@ def run_workload(ctx, name, steps, warmup, variant=1, want_e2e=True, want_parity
             ctx.barrier()
             total_ms += ctx.reduce(e0.elapsed_time(e1))
     launches = s.launch_count - l0
+    if N > 1:  # where this rank polled for its neighbours during the timed steps (+ the probe), per step
+        config["peer_wait_us_per_step_rank0"] = {k: [round(v[0] / max(steps, 1), 2), v[1]] for k, v in s.wait_stats().items()}
     clocks = sampler.stop()
     ms_per_step = total_ms / steps
     value = cells * steps / (total_ms * 1e-3)

@@ -126,6 +126,10 @@ int cfd_b200_debug_delay(cfd_b200_solver *s, double microseconds);
  * tail, 1 = one-way send of 2 rows of u, v + wait, 2 = the handshake exchange of the same rows, 3 = reduction with a row of
  * p riding on it); the caller times them with CUDA events on cfd_b200_stream(). */
 int cfd_b200_debug_comm(cfd_b200_solver *s, int kind, int reps);
+/* Measurement: microseconds spent polling for a peer GPU (us4[k]) and number of polls that found their data not yet there
+ * (count4[k]) since creation / the last call with reset != 0; k = 0 stand-alone wait kernels, 1 edge blocks of consumer
+ * kernels, 2 reductions, 3 handshake exchanges.  Edge blocks poll in parallel, so their sum is not elapsed time. */
+int cfd_b200_wait_stats(cfd_b200_solver *s, double *us4, long long *count4, int reset);
 /* Tuning / test hook: rows > 0 forces the streaming smoother with `rows` rows per strip on any grid size (the default,
  * 0, picks the strip height from the grid and uses the tile smoother on grids too small to fill the GPU). */
 int cfd_b200_set_smoother_strip(cfd_b200_solver *s, int rows);

@@ -143,6 +143,7 @@ def load_library(build: bool = True):
     L.cfd_b200_apply_shapes.argtypes = [S, C.POINTER(Shape), C.c_int]
     L.cfd_b200_set_smoother_strip.argtypes = [S, C.c_int]
     L.cfd_b200_comm_reset.argtypes = [S]
+    L.cfd_b200_wait_stats.argtypes = [S, _dp, C.POINTER(C.c_longlong), C.c_int]
     L.cfd_b200_debug_comm.argtypes = [S, C.c_int, C.c_int]
     L.cfd_b200_debug_delay.argtypes = [S, C.c_double]
     L.cfd_b200_smoother_strip_for.argtypes = [C.c_int, C.c_int, C.c_int]
@@ -232,6 +233,12 @@ class Solver:
     def comm_reset(self):
         """Collective over all slabs: clear a communication failure (CfdError -5) and restart the flag protocol."""
         self._check(self.L.cfd_b200_comm_reset(self.h))
+
+    def wait_stats(self, reset=True):
+        """{kind: (microseconds spent polling for a peer, polls that had to wait)} since the last reset (row slabs)."""
+        us, n = (C.c_double * 4)(), (C.c_longlong * 4)()
+        self._check(self.L.cfd_b200_wait_stats(self.h, us, n, int(reset)))
+        return {k: (us[i], n[i]) for i, k in enumerate(("wait_kernel", "edge_blocks", "reduce", "handshake"))}
 
     def debug_comm(self, kind: int, reps: int):
         """Measurement hook: enqueue `reps` slab-communication operations (see cfd_b200_debug_comm)."""

@@ -512,6 +512,8 @@ int halo_send(cfd_b200_solver *s, double *const *fields, const int *rows, const 
 }
 WaitArgs wait_args(const cfd_b200_solver *s, unsigned long long epoch) {
     WaitArgs w{};
+    static const int nowait = getenv("CFD_B200_DEBUG_NOWAIT") ? atoi(getenv("CFD_B200_DEBUG_NOWAIT")) : 0; // timing experiments only
+    if (nowait) return w;
     const int dirs = (int)(epoch >> 62);
     w.epoch = epoch & ((1ull << 62) - 1);
     if (!s->g.bottom && (dirs & HALO_UP)) w.f[0] = &s->blk[s->rank]->data_flag[0];  // rows sent UP by the slab below
@@ -1428,6 +1430,21 @@ int cfd_b200_debug_comm(cfd_b200_solver *s, int kind, int reps) {
     }
     s->halo_uv_valid = s->p_halo_valid = false;
     CU(cudaGetLastError());
+    return 0;
+}
+
+// Measurement: microseconds spent polling for a peer and number of polls that had to wait since the handle was created
+// (or since the last call with reset != 0), for the 4 kinds of waits of Scalars::wait_ns.  Synchronises the stream.
+int cfd_b200_wait_stats(cfd_b200_solver *s, double *us4, long long *count4, int reset) {
+    if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(s->h_sc, s->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    for (int k = 0; k < 4; ++k) {
+        if (us4) us4[k] = (double)s->h_sc->wait_ns[k] * 1e-3;
+        if (count4) count4[k] = (long long)s->h_sc->wait_n[k];
+    }
+    if (reset) CU(cudaMemsetAsync(s->d_sc->wait_ns, 0, sizeof(s->d_sc->wait_ns) + sizeof(s->d_sc->wait_n), s->stream));
     return 0;
 }
 

@@ -75,6 +75,9 @@ struct Scalars {
     double viz[4];          // k_viz_scalar: min, max, sum, sum of squares of the visualisation scalar
     int comm_error;         // a bounded peer wait ran out, or a peer reported that one of its waits did: results are invalid
     unsigned long long p2p_timeout_ns; // bound of every peer wait (CFD_B200_P2P_TIMEOUT_S, default 20 s)
+    // measurement (cfd_b200_wait_stats): time spent polling for a peer and number of polls that had to wait, per kind of
+    // consumer -- 0 stand-alone wait kernel, 1 a consumer kernel's edge blocks, 2 a reduction, 3 the handshake exchange
+    unsigned long long wait_ns[4], wait_n[4];
     int rb_redo;            // k_rbgs_stream met a non-finite value: the guarded tile kernel redoes this smooth()
 };
 
@@ -209,7 +212,7 @@ __device__ __forceinline__ unsigned long long p2p_now() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ bool p2p_wait(const unsigned long long *flag, unsigned long long epoch, Scalars *sc) {
+__device__ __forceinline__ bool p2p_wait(const unsigned long long *flag, unsigned long long epoch, Scalars *sc, int kind = 0) {
     const volatile unsigned long long *f = flag;
     bool ok = true;
     unsigned long long seen = *f;
@@ -221,6 +224,8 @@ __device__ __forceinline__ bool p2p_wait(const unsigned long long *flag, unsigne
                 break;
             }
         }
+        atomicAdd(&sc->wait_ns[kind], p2p_now() - t0);
+        atomicAdd(&sc->wait_n[kind], 1ull);
     }
     if (seen == P2P_POISON) ok = false; // the writer of this flag failed
     if (!ok) sc->comm_error = 1;
@@ -238,8 +243,8 @@ struct WaitArgs {
 __device__ __forceinline__ void p2p_wait_block(const WaitArgs &w, bool below, bool above, Scalars *sc) {
     if (!(below && w.f[0]) && !(above && w.f[1])) return; // block-uniform
     if (threadIdx.x + threadIdx.y * blockDim.x == 0) {
-        if (below && w.f[0]) p2p_wait(w.f[0], w.epoch, sc);
-        if (above && w.f[1]) p2p_wait(w.f[1], w.epoch, sc);
+        if (below && w.f[0]) p2p_wait(w.f[0], w.epoch, sc, 1);
+        if (above && w.f[1]) p2p_wait(w.f[1], w.epoch, sc, 1);
     }
     __syncthreads();
 }

@@ -109,8 +109,12 @@ template <int POW2, int VC>
 __global__ void __launch_bounds__(32 * RS_WARPS, RS_BLOCKS_PER_SM)
     k_rbgs_stream(Geom g, const double *__restrict__ pin, double *__restrict__ pout, const double *__restrict__ rhs,
                   Scalars *sc, double *partials, double tol, int RY, int nstrips, int finish, RsCoarse cz, WaitArgs hw) { pdl_begin();
+    // Strip of rows this block works on.  The first strip goes to the LAST blocks of the grid: on a row slab the strips at
+    // the slab's ends read the neighbours' rows, and by the time those blocks are scheduled the rows have long arrived
+    // (a block that waits at the start of the kernel delays everything queued behind it on its SM).
+    const int by = VC ? (int)blockIdx.y : (blockIdx.y + 1 == gridDim.y ? 0 : (int)blockIdx.y + 1);
     if (!VC) { // row slabs: only the strips at the slab's ends read the neighbours' 5 rows of p and rhs
-        const int yb0 = (g.bottom ? 0 : 1) + blockIdx.y * RY, yb1 = yb0 + RY - 1;
+        const int yb0 = (g.bottom ? 0 : 1) + by * RY, yb1 = yb0 + RY - 1;
         p2p_wait_block(hw, yb0 - RS_HY - 1 < 1, yb1 + RS_HY > g.ny, sc);
     }
     extern __shared__ __align__(16) double rs_raw[];
@@ -126,8 +130,8 @@ __global__ void __launch_bounds__(32 * RS_WARPS, RS_BLOCKS_PER_SM)
         const int a = X0 + 2 * lane;            // this lane's columns: a, a + 1
         // rows this launch stores: the slab's cell rows plus the ghost rows the slab owns (carried over unchanged)
         const int ylo = g.bottom ? 0 : 1, yhi = g.top ? g.ny + 1 : g.ny;
-        const int y0 = VC ? (blockIdx.y ? 1 + (int)blockIdx.y * RY : 0) : ylo + blockIdx.y * RY;
-        const int y1 = VC ? min(((int)blockIdx.y + 1) * RY, yhi) : min(y0 + RY - 1, yhi);
+        const int y0 = VC ? (by ? 1 + by * RY : 0) : ylo + by * RY;
+        const int y1 = VC ? min((by + 1) * RY, yhi) : min(y0 + RY - 1, yhi);
         // rows that may be updated: cells of this slab and, towards a neighbouring slab, its exchanged halo rows
         const int jlo = g.bottom ? 1 : 1 - RS_HY + 1, jhi = g.top ? g.ny : g.ny + RS_HY - 1;
         const bool c0 = a >= 1 && a <= g.nx, c1 = a + 1 >= 1 && a + 1 <= g.nx; // interior columns

@@ -75,8 +75,11 @@ template <int MODE>
 __global__ void __launch_bounds__(32 * MARCH_WARPS, MARCH_MINBLOCKS)
     k_rhs_march(Geom g, RhsConst k, const double *__restrict__ uin, const double *__restrict__ vin, const double *uacc,
                 const double *vacc, double *uout, double *vout, Scalars *sc, int XA, int XB, int YA, int YB, int RY, WaitArgs hw) { pdl_begin();
+    // the first strip of rows goes to the LAST blocks of the grid (see k_rbgs_stream: strips that wait for a neighbour's rows
+    // should be scheduled when the rows are there)
+    const int by = blockIdx.y + 1 == gridDim.y ? 0 : (int)blockIdx.y + 1;
     {   // row slabs: only the strips that read the neighbours' rows wait for them (rows y0-2 .. y1+3 are touched)
-        const int yb0 = YA + blockIdx.y * RY, yb1 = min(yb0 + RY - 1, YB);
+        const int yb0 = YA + by * RY, yb1 = min(yb0 + RY - 1, YB);
         p2p_wait_block(hw, yb0 - 2 < 1, yb1 + 3 > g.ny, sc);
     }
     const int lane = threadIdx.x & 31;
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS, MARCH_MINBLOCKS)
     const int X0 = XA - 2 + MARCH_COLS * wx; // raw column of lane 0's first column (odd => aligned double2)
     if (X0 + 2 > XB) return;                 // whole warp outside
     const int a = X0 + 2 * lane;             // this thread's columns: a, a+1
-    const int y0 = YA + blockIdx.y * RY;
+    const int y0 = YA + by * RY;
     const int y1 = min(y0 + RY - 1, YB);
     const bool loadable = (a + 1 <= g.P - CFD_XOFF - 1);
     const size_t P = g.P;

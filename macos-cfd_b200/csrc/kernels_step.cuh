@@ -307,7 +307,9 @@ __global__ void __launch_bounds__(RHS_TX *RHS_TY)
     __shared__ double us[(RHS_TY + 4) * S], vs[(RHS_TY + 4) * S];
     int rk = 0, first = 0;
     while (rk < rc.n - 1 && (int)blockIdx.x >= rc.end[rk]) first = rc.end[rk], ++rk;
-    const int t = blockIdx.x - first, tyr = t / rc.ntx[rk], txr = t - tyr * rc.ntx[rk];
+    const int t = blockIdx.x - first, nty = (rc.end[rk] - first) / rc.ntx[rk];
+    const int tyq = t / rc.ntx[rk], txr = t - tyq * rc.ntx[rk];
+    const int tyr = tyq + 1 == nty ? 0 : tyq + 1; // the first tile row of a rectangle goes last (see k_rbgs_stream)
     const int x0 = 1 + (rc.tx0[rk] + txr) * RHS_TX, y0 = 1 + (rc.ty0[rk] + tyr) * RHS_TY;
     p2p_wait_block(hw, y0 - 2 < 1, y0 + RHS_TY + 1 > g.ny, sc); // row slabs: tiles that read the neighbours' rows
     const int tid = threadIdx.y * RHS_TX + threadIdx.x;
@@ -505,8 +507,10 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256, PD_MINB)
     k_project_div(Geom g, const double *__restrict__ us, const double *__restrict__ vs, double *p, double *__restrict__ u,
                   double *__restrict__ v, double *__restrict__ rhs, Scalars *sc, double *partials, int rpb, WaitArgs hw) { pdl_begin();
+    // chunk of rows of this block; the first chunk goes to the LAST blocks of the grid (see k_rbgs_stream)
+    const int by = blockIdx.y + 1 == gridDim.y ? 0 : (int)blockIdx.y + 1;
     // row slabs: the chunks at the slab's ends read the neighbours' p row (and the top one the v* row above the slab)
-    p2p_wait_block(hw, blockIdx.y == 0, 1 + (int)(blockIdx.y + 1) * rpb > g.ny, sc);
+    p2p_wait_block(hw, by == 0, 1 + (by + 1) * rpb > g.ny, sc);
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
         const double res = sc->res; // last_residual_ = isfinite(res) ? res : 1e9 (pressure.cpp:123, :232)
         if (!finite_d(res)) {
@@ -518,7 +522,7 @@ __global__ void __launch_bounds__(256, PD_MINB)
     const int lane = threadIdx.x & 31;
     const bool active = ii <= g.nx + 1;
     const double dt = sc->dt, idx = g.idx, idy = g.idy;
-    const int jbase = 1 + blockIdx.y * rpb;
+    const int jbase = 1 + by * rpb;
     // v rows: up to ny+1 on every slab.  Below another slab that row belongs to the neighbour; it is projected here as well
     // (its vs and p rows were delivered) and stored into the halo row, so that the top cell row closes without waiting
     // for the neighbour's projection -- the same expression on the same operands, hence the same bits.

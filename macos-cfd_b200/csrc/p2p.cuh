@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) k_halo_xchg(HaloArgs a, P2PBlock *me, Sca
     if (tid < 2) {
         if (blockIdx.x == 0 && a.peer_enter[tid]) p2p_signal(a.peer_enter[tid], a.epoch, sc);
         bool ok = true;
-        if (a.peer_enter[tid]) ok = p2p_wait(&me->enter_flag[tid], a.epoch, sc);
+        if (a.peer_enter[tid]) ok = p2p_wait(&me->enter_flag[tid], a.epoch, sc, 3);
         if (tid == 0) s_go = 1;
         __syncwarp(0x3);
         if (!ok) s_go = 0;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) k_halo_xchg(HaloArgs a, P2PBlock *me, Sca
     // 3. the last block: all rows of all blocks are out -> data flags, then wait for the neighbours' rows
     if (tid < 2 && a.peer_data[tid]) {
         p2p_signal(a.peer_data[tid], a.epoch, sc);
-        p2p_wait(&me->data_flag[tid], a.epoch, sc);
+        p2p_wait(&me->data_flag[tid], a.epoch, sc, 3);
     }
     if (tid == 0) me->ticket = 0u;
 }
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(P2P_RED_THREADS) k_p2p_reduce(RedArgs a, Scala
         volatile double *slot = dst->red_val[par][a.rank];
         slot[0] = v0, slot[1] = v1, slot[2] = v2, slot[3] = v3, slot[4] = v4;
         p2p_signal(&dst->red_flag[par][a.rank], a.epoch, sc);
-        p2p_wait(&me->red_flag[par][t], a.epoch, sc);
+        p2p_wait(&me->red_flag[par][t], a.epoch, sc, 2);
     }
     __syncthreads();
     if (t == 0) {
@@ -232,6 +232,6 @@ __global__ void __launch_bounds__(P2P_RED_THREADS) k_p2p_reduce(RedArgs a, Scala
     __syncthreads();
     if (t < 2 && a.peer_data[t]) {
         p2p_signal(a.peer_data[t], a.hepoch, sc);
-        p2p_wait(&me->data_flag[t], a.hepoch, sc);
+        p2p_wait(&me->data_flag[t], a.hepoch, sc, 2);
     }
 }
