@@ -105,6 +105,7 @@ struct cfd_b200_solver {
     // V-cycle extension: coarse levels (level 0 aliases p / rhs), allocated on first use
     int mg_nlev = 0;
     MgLevel mg[MG_CTA_MAXLEV + 4] = {};
+    MgLevel mg_gather = {}; // row slabs: the whole first one-block level, gathered onto every slab
     int mg_cta_smem_max = 0;
     // cooperative persistent PCG (small grids)
     double *coop_xrows = nullptr, *coop_slots = nullptr;
@@ -592,6 +593,10 @@ int reduce_fin(cfd_b200_solver *s, int kind, double tol, int max_iters, double *
         TRY(allreduce(s, s->d_sc->red, 1, ncclSum));
         LAUNCH(s, k_rbgs_fin, 1, 1, s->d_sc, tol);
         break;
+    case RED_VC:
+        TRY(allreduce(s, s->d_sc->red, 1, ncclSum));
+        LAUNCH(s, k_mg_norm_fin, 1, 1, s->d_sc, tol);
+        break;
     case RED_STEP_END: // one collective: CFL maxima of the next step + the two partial sums of squares
         LAUNCH(s, k_slab_pack, 1, 1, s->d_sc);
         NCCLCHK(nccl_api().AllGather(s->d_sc->red, s->gathered, 4, ncclDouble, s->comm, s->stream));
@@ -691,9 +696,152 @@ int vcycle_levels(int nx, int ny, int mg_levels) {
     while (n < mg_levels && n < MG_CTA_MAXLEV + 3 && nx % 2 == 0 && ny % 2 == 0 && nx / 2 >= 4 && ny / 2 >= 4) nx /= 2, ny /= 2, ++n;
     return n;
 }
+// The same V-cycle on row slabs.  Every level is split like the fine grid (its rows are the slab's rows halved l times, so
+// a 2x2 block of children never straddles two slabs); the neighbours' row of p is exchanged after every kernel that changes
+// p on a level (NCCL send/recv: the coarse levels live outside the IPC-mapped arena); the levels that fit into one block's
+// shared memory are gathered onto EVERY slab (all-gather of the restricted right-hand side), solved there redundantly by
+// the same one-block kernel, and each slab takes its rows (and the two rows next to them) of the result.  Every update
+// sees the operands the single-GPU cycle sees, so p is bit-identical to it; only the residual norm is summed in another
+// order.  One launch per colour pass on every level (the streaming sweeps of the single-GPU path are not slab-aware yet).
+int enqueue_vcycle_slab(cfd_b200_solver *s, const cfd_b200_params *pp, double Lx, double Ly, bool in_step) {
+    const Geom &g = s->g;
+    NcclApi &nc = nccl_api();
+    const int nlev = vcycle_levels(g.nx, g.ny_glob, pp->mg_levels), sweeps = pp->rbgs_sweeps;
+    if (g.ny_glob % s->nranks != 0 || (g.ny & ((1 << (nlev - 1)) - 1)) != 0)
+        return fail(CFD_B200_EUNSUPPORTED, "mg_mode=VCYCLE on %d slabs with %d levels needs ny divisible by %d (ny = %d)", s->nranks,
+                    nlev, s->nranks << (nlev - 1), g.ny_glob);
+    join_comm(s);
+    for (int l = 0; l < nlev; ++l) {
+        MgLevel &L = s->mg[l];
+        const int nx = g.nx >> l, ny = g.ny >> l, nyg = g.ny_glob >> l;
+        if (l > 0 && (L.nx != nx || L.ny != ny || !L.p)) {
+            if (L.p) cudaFree(L.p), cudaFree(L.rhs), cudaFree(L.alt);
+            L.P = ((nx + 3 + CFD_XOFF + 2) + 15) / 16 * 16;
+            const size_t n = (size_t)L.P * (ny + 3 + 2 * CFD_YOFF);
+            CU(cudaMalloc(&L.p, n * sizeof(double)));
+            CU(cudaMalloc(&L.rhs, n * sizeof(double)));
+            L.alt = nullptr;
+            CU(cudaMemsetAsync(L.p, 0, n * sizeof(double), s->stream));
+            CU(cudaMemsetAsync(L.rhs, 0, n * sizeof(double), s->stream));
+        }
+        L.nx = nx, L.ny = ny;
+        const double dx = Lx / static_cast<double>(nx), dy = Ly / static_cast<double>(nyg);
+        L.idx2 = 1.0 / (dx * dx);
+        L.idy2 = 1.0 / (dy * dy);
+        L.denom = 2.0 * (L.idx2 + L.idy2);
+        if (l == 0) L.P = g.P, L.p = s->p, L.rhs = s->rhs, L.alt = s->p_alt;
+        L.j0 = g.j0 >> l, L.bottom = g.bottom, L.top = g.top;
+    }
+    if (nlev > s->mg_nlev) s->mg_nlev = nlev;
+    // first level that (with everything below it) fits into one block's shared memory -- sizes of the WHOLE level
+    MgCtaPlan plan{};
+    int lc = nlev;
+    for (int l = 1; l < nlev; ++l) {
+        size_t doubles = 0;
+        for (int m = l; m < nlev; ++m) doubles += 2 * (size_t)((g.nx >> m) + 2) * ((g.ny_glob >> m) + 2);
+        if (doubles * 8 <= 200 * 1024 && nlev - l <= MG_CTA_MAXLEV) {
+            lc = l;
+            break;
+        }
+    }
+    int cta_smem = 0;
+    MgLevel &G = s->mg_gather; // the whole level lc, on every slab
+    if (lc < nlev) {
+        plan.nlev = nlev - lc;
+        plan.sweeps = sweeps;
+        int off = 0;
+        for (int m = lc; m < nlev; ++m) {
+            const int k = m - lc, nx = g.nx >> m, nyg = g.ny_glob >> m;
+            const double dx = Lx / static_cast<double>(nx), dy = Ly / static_cast<double>(nyg);
+            plan.nx[k] = nx, plan.ny[k] = nyg, plan.off[k] = off;
+            plan.idx2[k] = 1.0 / (dx * dx), plan.idy2[k] = 1.0 / (dy * dy), plan.denom[k] = 2.0 * (plan.idx2[k] + plan.idy2[k]);
+            off += 2 * (nx + 2) * (nyg + 2);
+        }
+        cta_smem = off * 8;
+        if (cta_smem > s->mg_cta_smem_max) {
+            CU(cudaFuncSetAttribute(k_mg_coarse_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, cta_smem));
+            s->mg_cta_smem_max = cta_smem;
+        }
+        const MgLevel &C = s->mg[lc];
+        const int nyg = g.ny_glob >> lc;
+        if (G.nx != C.nx || G.ny != nyg || !G.p) {
+            if (G.p) cudaFree(G.p), cudaFree(G.rhs);
+            const size_t n = (size_t)C.P * (nyg + 3 + 2 * CFD_YOFF);
+            CU(cudaMalloc(&G.p, n * sizeof(double)));
+            CU(cudaMalloc(&G.rhs, n * sizeof(double)));
+            CU(cudaMemsetAsync(G.p, 0, n * sizeof(double), s->stream));
+            CU(cudaMemsetAsync(G.rhs, 0, n * sizeof(double), s->stream));
+        }
+        G = MgLevel{C.nx, nyg, C.P, C.idx2, C.idy2, C.denom, G.p, G.rhs, nullptr, 0, 1, 1};
+    }
+    // the neighbours' row of L.p (1 row both ways)
+    auto xchg = [&](const MgLevel &L) -> int {
+        const size_t cnt = (size_t)L.P;
+        auto row = [&](int jj) { return L.p + (size_t)(jj + CFD_YOFF) * L.P; };
+        NCCLCHK(nc.GroupStart());
+        if (!g.top) {
+            NCCLCHK(nc.Send(row(L.ny), cnt, ncclDouble, s->rank + 1, s->comm, s->stream));
+            NCCLCHK(nc.Recv(row(L.ny + 1), cnt, ncclDouble, s->rank + 1, s->comm, s->stream));
+        }
+        if (!g.bottom) {
+            NCCLCHK(nc.Send(row(1), cnt, ncclDouble, s->rank - 1, s->comm, s->stream));
+            NCCLCHK(nc.Recv(row(0), cnt, ncclDouble, s->rank - 1, s->comm, s->stream));
+        }
+        NCCLCHK(nc.GroupEnd());
+        return 0;
+    };
+    auto smooth = [&](int l, int n) -> int {
+        const MgLevel &L = s->mg[l];
+        dim3 block(32, 8), cgrid(cdiv(cdiv(L.nx + 1, 2), 32), cdiv(L.ny, 8));
+        for (int k = 0; k < n; ++k)
+            for (int colour = 0; colour < 2; ++colour) {
+                LAUNCH(s, k_mg_colour, cgrid, block, L, colour, s->d_sc);
+                TRY(xchg(L));
+            }
+        return 0;
+    };
+    if (!in_step) LAUNCH(s, k_solve_begin, 1, 1, s->d_sc);
+    LAUNCH(s, k_mg_zero_ghosts, cdiv((g.nx > g.ny ? g.nx : g.ny) + 2, 128), 128, s->mg[0], s->d_sc);
+    TRY(xchg(s->mg[0]));
+    const int top = lc < nlev ? lc : nlev - 1; // levels [0, top) run as global-memory kernels on the way down
+    for (int vc = 0; vc < pp->vcycles; ++vc) {
+        for (int l = 0; l < top; ++l) {
+            TRY(smooth(l, sweeps));
+            const MgLevel &F = s->mg[l], &C = s->mg[l + 1];
+            LAUNCH(s, k_mg_restrict, dim3(cdiv(C.nx, 32), cdiv(C.ny, 8)), dim3(32, 8), F, C, s->d_sc);
+            if (l + 1 < top || lc >= nlev) TRY(xchg(C)); // the zeroed guess (a level handed to the one-block kernel gets its rows back below)
+        }
+        if (lc < nlev) {
+            const MgLevel &C = s->mg[lc];
+            // my rows of the restricted right-hand side into the whole-level array, all-gather in place, the coarse part of
+            // the V in one block, my rows of the result (+ the row on either side, for the prolongation) back
+            const size_t cnt = (size_t)C.P * C.ny, r0 = (size_t)(1 + C.j0 + CFD_YOFF) * C.P;
+            CU(cudaMemcpyAsync(G.rhs + r0, C.rhs + (size_t)(1 + CFD_YOFF) * C.P, cnt * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+            NCCLCHK(nc.AllGather(G.rhs + r0, G.rhs + (size_t)(1 + CFD_YOFF) * C.P, cnt, ncclDouble, s->comm, s->stream));
+            launch_k(s, k_mg_coarse_cta, dim3(1), dim3(1024), (size_t)cta_smem, G, plan, s->d_sc);
+            CU(cudaMemcpyAsync(C.p + (size_t)CFD_YOFF * C.P, G.p + (size_t)(C.j0 + CFD_YOFF) * C.P, (size_t)C.P * (C.ny + 2) * sizeof(double),
+                               cudaMemcpyDeviceToDevice, s->stream));
+        } else {
+            TRY(smooth(nlev - 1, nlev == 1 ? sweeps : 16 * sweeps));
+        }
+        for (int l = top - 1; l >= 0; --l) {
+            const MgLevel &F = s->mg[l];
+            LAUNCH(s, k_mg_prolong, dim3(cdiv(F.nx, 32), cdiv(F.ny, 8)), dim3(32, 8), F, s->mg[l + 1], s->d_sc);
+            TRY(xchg(F));
+            TRY(smooth(l, sweeps));
+        }
+        const MgLevel &L0 = s->mg[0];
+        dim3 rgrid(cdiv(L0.nx, 256), L0.ny < 256 ? L0.ny : 256);
+        LAUNCH(s, k_mg_residual_norm, rgrid, 256, L0, s->d_sc, s->partials, pp->tol, 0);
+        TRY(reduce_fin(s, RED_VC, pp->tol, 0));
+    }
+    if (!in_step) LAUNCH(s, k_solve_finish, 1, 1, s->d_sc);
+    return 0;
+}
+
 int enqueue_vcycle(cfd_b200_solver *s, const cfd_b200_params *pp, double Lx, double Ly, bool in_step) {
     const Geom &g = s->g;
-    if (s->nranks > 1) return fail(CFD_B200_EUNSUPPORTED, "mg_mode=VCYCLE is single-GPU in this version");
+    if (s->nranks > 1) return enqueue_vcycle_slab(s, pp, Lx, Ly, in_step);
     const int nlev = vcycle_levels(g.nx, g.ny, pp->mg_levels);
     const int sweeps = pp->rbgs_sweeps;
     for (int l = 0; l < nlev; ++l) { // geometry of every level exactly as the restatement computes it
@@ -717,6 +865,7 @@ int enqueue_vcycle(cfd_b200_solver *s, const cfd_b200_params *pp, double Lx, dou
         L.idy2 = 1.0 / (dy * dy);
         L.denom = 2.0 * (L.idx2 + L.idy2);
         if (l == 0) L.P = g.P, L.p = s->p, L.rhs = s->rhs, L.alt = s->p_alt;
+        L.j0 = 0, L.bottom = L.top = 1;
     }
     if (nlev > s->mg_nlev) s->mg_nlev = nlev;
     // first level that (with everything below it) fits into one block's shared memory
@@ -793,7 +942,7 @@ int enqueue_vcycle(cfd_b200_solver *s, const cfd_b200_params *pp, double Lx, dou
             LAUNCH(s, k_mg_restrict, dim3(cdiv(C.nx, 32), cdiv(C.ny, 8)), dim3(32, 8), L, C, s->d_sc);
         } else {
             dim3 rgrid(cdiv(L.nx, 256), L.ny < 256 ? L.ny : 256);
-            LAUNCH(s, k_mg_residual_norm, rgrid, 256, L, s->d_sc, s->partials, pp->tol);
+            LAUNCH(s, k_mg_residual_norm, rgrid, 256, L, s->d_sc, s->partials, pp->tol, 1);
         }
     };
     if (!in_step) LAUNCH(s, k_solve_begin, 1, 1, s->d_sc);
@@ -1266,6 +1415,7 @@ void cfd_b200_destroy(cfd_b200_solver *s) {
         if (s->mg[l].rhs) cudaFree(s->mg[l].rhs);
         if (s->mg[l].alt) cudaFree(s->mg[l].alt);
     }
+    if (s->mg_gather.p) cudaFree(s->mg_gather.p), cudaFree(s->mg_gather.rhs);
     if (s->viz_rgb) cudaFree(s->viz_rgb);
     double *fields[] = {s->arena, s->scratch_u, s->scratch_v, s->partials, s->viz_out};
     for (double *f : fields)

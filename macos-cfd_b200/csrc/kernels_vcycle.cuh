@@ -13,10 +13,13 @@
 #include "common.cuh"
 
 struct MgLevel {
-    int nx, ny, P;
+    int nx, ny, P;   // ny: LOCAL cell rows of the level (the whole level on a single-GPU handle)
     double idx2, idy2, denom;
     double *p, *rhs; // device arrays in the common padded layout (ghost ring = 0)
     double *alt;     // ping-pong partner of p (streaming sweeps); level 0: the State's p_alt
+    // row slabs: global index of local cell row 1 minus 1 (parity of the colours), and whether the slab touches the
+    // domain's bottom / top wall (a slab-internal boundary is a halo row, not a wall); 0 / 1 / 1 on a single GPU
+    int j0, bottom, top;
 };
 __host__ __device__ __forceinline__ size_t mg_idx(const MgLevel &L, int ii, int jj) {
     return (size_t)(jj + CFD_YOFF) * (size_t)L.P + (size_t)(ii + CFD_XOFF);
@@ -25,13 +28,17 @@ __device__ __forceinline__ double mg_wall(int nx, int ny, double idx2, double id
     int bx = (ii == 1) + (ii == nx), by = (jj == 1) + (jj == ny);
     return (double)bx * idx2 + (double)by * idy2;
 }
+__device__ __forceinline__ double mg_wall(const MgLevel &L, int ii, int jj) { // the same term on one slab of the level
+    int bx = (ii == 1) + (ii == L.nx), by = (L.bottom && jj == 1) + (L.top && jj == L.ny);
+    return (double)bx * L.idx2 + (double)by * L.idy2;
+}
 
 // ---------------------------------------------------------------- generic (any level) global-memory kernels
 __global__ void k_mg_zero_ghosts(MgLevel L, const Scalars *sc) { pdl_begin();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t <= L.nx + 1) {
-        L.p[mg_idx(L, t, 0)] = 0.0;
-        L.p[mg_idx(L, t, L.ny + 1)] = 0.0;
+        if (L.bottom) L.p[mg_idx(L, t, 0)] = 0.0;
+        if (L.top) L.p[mg_idx(L, t, L.ny + 1)] = 0.0;
     }
     if (t <= L.ny + 1) {
         L.p[mg_idx(L, 0, t)] = 0.0;
@@ -43,19 +50,19 @@ __global__ void __launch_bounds__(256) k_mg_colour(MgLevel L, int colour, const 
     if (sc->done) return;
     const int jj = 1 + blockIdx.y * blockDim.y + threadIdx.y;
     if (jj > L.ny) return;
-    const int ii = 1 + 2 * (blockIdx.x * blockDim.x + threadIdx.x) + ((jj - 1 + colour) & 1);
+    const int ii = 1 + 2 * (blockIdx.x * blockDim.x + threadIdx.x) + ((L.j0 + jj - 1 + colour) & 1);
     if (ii > L.nx) return;
     const size_t o = mg_idx(L, ii, jj);
     const double *q = L.p + o;
     double sum = (q[1] + q[-1]) * L.idx2 + (q[L.P] + q[-L.P]) * L.idy2;
-    L.p[o] = (sum - L.rhs[o]) / (L.denom + mg_wall(L.nx, L.ny, L.idx2, L.idy2, ii, jj));
+    L.p[o] = (sum - L.rhs[o]) / (L.denom + mg_wall(L, ii, jj));
 }
 
 __device__ __forceinline__ double mg_resid(const MgLevel &L, int ii, int jj) {
     const size_t o = mg_idx(L, ii, jj);
     const double *q = L.p + o;
     double Ap = (q[1] - 2.0 * q[0] + q[-1]) * L.idx2 + (q[L.P] - 2.0 * q[0] + q[-L.P]) * L.idy2;
-    Ap = Ap - mg_wall(L.nx, L.ny, L.idx2, L.idy2, ii, jj) * q[0];
+    Ap = Ap - mg_wall(L, ii, jj) * q[0];
     return L.rhs[o] - Ap;
 }
 
@@ -84,7 +91,14 @@ __global__ void __launch_bounds__(256) k_mg_prolong(MgLevel F, MgLevel C, const 
 }
 
 // ||rhs - L p||_2 of the fine level after a cycle, and the cycle loop's exit test
-__global__ void __launch_bounds__(256) k_mg_residual_norm(MgLevel L, Scalars *sc, double *partials, double tol) { pdl_begin();
+// (finish = 0 on row slabs: the local sum goes to Scalars::red[0] and the reduction over the slabs runs the same tail)
+__device__ __forceinline__ void mg_norm_tail(Scalars *sc, double sum, double tol) {
+    double res = sqrt(sum);
+    sc->res = res;
+    sc->iters = sc->iters + 1;
+    if (res < tol) sc->done = 1;
+}
+__global__ void __launch_bounds__(256) k_mg_residual_norm(MgLevel L, Scalars *sc, double *partials, double tol, int finish) { pdl_begin();
     if (sc->done) return;
     const int ii = 1 + blockIdx.x * blockDim.x + threadIdx.x;
     double acc[1] = {0.0};
@@ -94,12 +108,11 @@ __global__ void __launch_bounds__(256) k_mg_residual_norm(MgLevel L, Scalars *sc
             acc[0] += r * r;
         }
     grid_sum<1>(acc, partials, &sc->ticket[2], [=](double(&t)[1]) {
-        double res = sqrt(t[0]);
-        sc->res = res;
-        sc->iters = sc->iters + 1;
-        if (res < tol) sc->done = 1;
+        if (finish) mg_norm_tail(sc, t[0], tol);
+        else sc->red[0] = t[0];
     });
 }
+__global__ void k_mg_norm_fin(Scalars *sc, double tol) { pdl_begin(); if (!sc->done) mg_norm_tail(sc, sc->red[0], tol); }
 
 // ---------------------------------------------------------------- CTA-resident coarse part of the V
 #define MG_CTA_MAXLEV 12

@@ -142,7 +142,8 @@ enum {
     RED_RBGS,         // 1 sum   -> rbgs_tail
     RED_STEP_END,     // max|u|, max|v|, sum div^2 before / after (end of a step); + the deferred residual sum of the last smooth()
     RED_CFL,          // max|u|, max|v| (compute_cfl after an upload)
-    RED_DIAG          // divergence_l2 sum + max_velocity max
+    RED_DIAG,         // divergence_l2 sum + max_velocity max
+    RED_VC            // 1 sum   -> mg_norm_tail (true V-cycle on row slabs: residual norm after a cycle)
 };
 struct RedArgs {
     P2PBlock *blk[P2P_MAXR]; // every rank's block (blk[rank] = mine)
@@ -204,6 +205,7 @@ __global__ void __launch_bounds__(P2P_RED_THREADS) k_p2p_reduce(RedArgs a, Scala
     case RED_PCG1: if (!sc->done) pcg_tail1(sc, r0); break;
     case RED_PCG2: if (!sc->done) pcg_tail2(sc, r0, r1, a.tol, a.max_iters); break;
     case RED_RBGS: if (!sc->done) rbgs_tail(sc, r0, a.tol); break;
+    case RED_VC: if (!sc->done) mg_norm_tail(sc, r0, a.tol); break;
     case RED_STEP_END:
         sc->div_before = r2, sc->div_after = r3;
         if (a.defer_rbgs && !sc->done) { // the last smooth() of the step: no decision of the step depended on its residual

@@ -39,7 +39,8 @@ def run_single(kw):
     s.set_smoother_strip(kw.get("strip", 0))
     if kw["preset"] == "shear":
         s.upload(u=cfd.shear_initial_u(kw["nx"], kw["ny"], kw.get("Ly", 1.0)))
-    pp = cfd.make_params(kw["solver"], vcycles=2, tol=1e-8, pcg_max_iters=kw.get("iters", 200))
+    pp = cfd.make_params(kw["solver"], vcycles=kw.get("vcycles", 2), tol=kw.get("tol", 1e-8), pcg_max_iters=kw.get("iters", 200),
+                         mg_levels=kw.get("mg_levels", 3), rbgs_sweeps=kw.get("sweeps", 2), mg_mode=kw.get("mg_mode", 0))
     hist = []
     for _ in range(kw["steps"]):
         i = s.step(bc, Re, CFL, pp)
@@ -102,3 +103,20 @@ def test_slabs_with_a_late_rank_and_a_comm_reset(tmp_path, preset, solver, delay
             assert same(got[name], a), name
         else:
             assert np.linalg.norm(got[name] - a) <= 1e-10 * np.linalg.norm(a), name
+
+
+@pytest.mark.parametrize("preset,nx,ny,levels,sweeps,vcycles", [("lid", 256, 192, 5, 2, 3), ("jet", 512, 256, 7, 1, 2),
+                                                                ("shear", 128, 128, 3, 3, 4)])
+def test_true_vcycle_on_slabs_matches_single_gpu(tmp_path, preset, nx, ny, levels, sweeps, vcycles):
+    """mg_mode = VCYCLE (the true geometric V-cycle extension) on row slabs: every level split like the fine grid, the
+    one-block coarse part gathered onto every slab -- u, v, p bit-identical to one GPU after whole time steps."""
+    n = min(ngpu(), 4)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    kw = dict(preset=preset, solver="mg", nx=nx, ny=ny, steps=3, vcycles=vcycles, tol=1e-9)
+    got = run_slabs(n, tmp_path, variant=1, p2p=1, **{"mg-mode": 1, "mg-levels": levels, "sweeps": sweeps}, **kw)
+    hist, (u, v, p, rhs), div_l2, vmax = run_single(dict(kw, mg_mode=1, mg_levels=levels, sweeps=sweeps))
+    assert np.array_equal(got["hist"][:, 0], hist[:, 0]) and np.array_equal(got["hist"][:, 2], hist[:, 2])  # dt, cycles
+    for name, a in (("u", u), ("v", v), ("p", p), ("rhs", rhs)):
+        assert same(got[name], a), name
+    assert np.allclose(got["hist"][:, 1], hist[:, 1], rtol=1e-10)
