@@ -340,7 +340,7 @@ def slab_parity(ctx, name, s, reset, bc, Re, CFL, pp, steps=2):
     return out
 
 
-def run_workload(ctx, name, steps, warmup, variant=1, want_e2e=True, want_parity=True):
+def run_workload(ctx, name, steps, warmup, variant=1, want_e2e=True, want_parity=True, want_solves=False):
     """Measure one workload; returns the fields of its JSON entry (identical on every rank up to rank-0-only details)."""
     import numpy as np
     torch, cfd, N = ctx.torch, ctx.cfd, ctx.N
@@ -481,7 +481,7 @@ def run_workload(ctx, name, steps, warmup, variant=1, want_e2e=True, want_parity
     top = max((k for k in acc if stage_bytes.get(k)), key=lambda k: acc[k])
     if top == "pressure_solve":  # the stage is `launches` identical kernel launches (mg) / iterations (PCG)
         launches_top = max(pinfo.iters, 1)
-        kernel = s.last_smoother if solver == "mg" else PCG_KERNEL
+        kernel = s.last_smoother if solver == "mg" else s.last_pcg
         bytes_launch = (24 if solver == "mg" else 64) * cells_rank
     else:
         launches_top, kernel, bytes_launch = 1, STAGE_KERNEL[top], stage_bytes[top] * cells_rank
@@ -532,6 +532,29 @@ def run_workload(ctx, name, steps, warmup, variant=1, want_e2e=True, want_parity
     parity = None
     if N > 1 and want_parity:
         parity = slab_parity(ctx, name, s, reset, bc, Re, CFL, pp)
+    solves = None
+    if want_solves:  # BASELINE configs[4]: "PCG vs MG pressure-solve time" -- the same right-hand side, from p = 0
+        reset()
+        for _ in range(2):
+            s.step(bc, Re, CFL, pp)
+        rhs = s.download()[3]
+        solves = []
+        for label, sp in (("mg as the reference runs it: 2 x smooth() on the fine grid", cfd.make_params("mg", vcycles=2, tol=0.0)),
+                          ("Jacobi-PCG, 200 iterations", cfd.make_params("pcg", tol=0.0, pcg_max_iters=200)),
+                          ("true V-cycle (extension, parity unpinned): 2 x V(2,2), 8 levels",
+                           cfd.make_params("mg", vcycles=2, tol=0.0, mg_levels=8, rbgs_sweeps=2, mg_mode=cfd.MG_VCYCLE))):
+            best, res, it = None, None, None
+            for _ in range(2):
+                s.upload(p=zero["p"], rhs=rhs)
+                ctx.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                res, it = s.pressure_solve(sp)
+                e1.record(stream)
+                e1.synchronize()
+                t = ctx.reduce(e0.elapsed_time(e1))
+                best = t if best is None else min(best, t)
+            solves.append({"solver": label, "ms": round(best, 3), "residual": res, "iterations": it})
     s.close()
     del flush
     torch.cuda.empty_cache()
@@ -541,6 +564,8 @@ def run_workload(ctx, name, steps, warmup, variant=1, want_e2e=True, want_parity
            "last_step": {"dt": info.dt, "residual": info.residual, "iters": info.iters}}
     if parity is not None:
         out["parity"] = parity
+    if solves is not None:
+        out["pressure_solve_times"] = solves
     return out
 
 
@@ -596,7 +621,8 @@ def main():
         return
 
     ctx = Ctx(N)
-    main_r = run_workload(ctx, args.workload, args.steps, args.warmup, args.variant, not args.no_e2e, not args.no_parity)
+    main_r = run_workload(ctx, args.workload, args.steps, args.warmup, args.variant, not args.no_e2e, not args.no_parity,
+                          want_solves=not args.no_also and args.workload == DEFAULT_WORKLOAD)
     line = dict(base, **main_r)
     if not args.no_also:
         also = []

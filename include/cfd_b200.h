@@ -139,6 +139,10 @@ int cfd_b200_smoother_strip_for(int nx, int ny, int sm_count);
 /* Which kernel ran the last smooth() of --solver=mg (reference mode): 1 = streaming smoother (large grids), 2 = tile
  * smoother (small grids, and the guarded slow path of 1), 3 = one launch per colour pass (variant 0), 0 = none yet. */
 int cfd_b200_last_smoother(const cfd_b200_solver *s);
+/* Which kernels ran the last PCG solve: 1 = k_pcg_coop (the whole solve in one cooperative persistent launch; grids whose
+ * p, r, s fit into the SMs' shared memory), 2 = the streaming pair k_pcg_phase1_march / _phase2_march, 3 = the tile pair
+ * k_pcg_phase1 / _phase2, 0 = none yet. */
+int cfd_b200_last_pcg(const cfd_b200_solver *s);
 /* First owned cell row and number of owned cell rows of this handle (0, ny for a single-GPU handle). */
 int cfd_b200_slab_rows(const cfd_b200_solver *s, int *row0, int *nrows);
 

@@ -138,6 +138,7 @@ def load_library(build: bool = True):
     L.cfd_b200_slab_rows.argtypes = [S, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.cfd_b200_comm_mode.argtypes = [S]
     L.cfd_b200_last_smoother.argtypes = [S]
+    L.cfd_b200_last_pcg.argtypes = [S]
     L.cfd_b200_compute_scalar.argtypes = [S, C.c_int, C.c_void_p, C.POINTER(FieldStats)]
     L.cfd_b200_render_rgb.argtypes = [S, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p]
     L.cfd_b200_apply_shapes.argtypes = [S, C.POINTER(Shape), C.c_int]
@@ -256,6 +257,12 @@ class Solver:
     def last_smoother(self) -> str:
         """Kernel that ran the last smooth() of the reference-mode mg solver."""
         return ("none", "k_rbgs_stream", "k_rbgs_fused", "k_rbgs_colour x4 + k_rbgs_residual")[self.L.cfd_b200_last_smoother(self.h)]
+
+    @property
+    def last_pcg(self) -> str:
+        """Kernels that ran the last PCG solve."""
+        return ("none", "k_pcg_coop (whole solve, one cooperative launch)", "k_pcg_phase1_march + k_pcg_phase2_march (one iteration)",
+                "k_pcg_phase1 + k_pcg_phase2 (one iteration)")[self.L.cfd_b200_last_pcg(self.h)]
 
     def _check(self, rc):
         if rc != 0:

@@ -80,6 +80,7 @@ struct cfd_b200_solver {
     int variant = 1;
     int rb_strip = 0;      // > 0: force the streaming smoother with this many rows per strip (tests, tuning)
     int last_smoother = 0; // which kernel ran the last smooth(): 1 streaming, 2 tile, 3 per-colour passes
+    int last_pcg = 0;      // which kernels ran the last PCG solve: 1 cooperative persistent, 2 streaming, 3 tiles
     int pdl = 3; // programmatic dependent launch between consecutive kernels (bit mask, see cfd_b200_create_slab; CFD_B200_PDL=0 turns it off)
     bool cfl_cached = false;   // umax/vmax of the current device State are already in d_sc (from the last step)
     cfd_b200_bc last_bc{};
@@ -1003,6 +1004,7 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp, bool in_step = 
             CU(cudaLaunchCooperativeKernel((void *)k_pcg_coop, dim3(s->coop_blocks), dim3(PC_THREADS), args,
                                            (size_t)s->coop_smem, s->stream));
             s->launches++;
+            s->last_pcg = 1;
             if (!in_step) LAUNCH(s, k_solve_finish, 1, 1, s->d_sc);
             return 0;
         }
@@ -1027,6 +1029,7 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp, bool in_step = 
         if (ry_env > 0) RY = ry_env;
         const dim3 mgrid(gxm, cdiv(g.ny, RY));
         const bool march = s->variant != 0 && (ry_env > 0 || (long long)g.nx * g.ny >= (2LL << 20));
+        s->last_pcg = march ? 2 : 3;
         for (int it = 0; it < pp->pcg_max_iters; ++it) {
             if (march)
                 LAUNCH(s, k_pcg_phase1_march, mgrid, 32 * PM_WARPS, g, s->r, s_old, s_new, s->d_sc, s->partials, RY, single);
@@ -1610,6 +1613,7 @@ int cfd_b200_smoother_strip_for(int nx, int ny, int sm_count) {
 }
 
 int cfd_b200_last_smoother(const cfd_b200_solver *s) { return s ? s->last_smoother : 0; }
+int cfd_b200_last_pcg(const cfd_b200_solver *s) { return s ? s->last_pcg : 0; }
 
 int cfd_b200_comm_mode(const cfd_b200_solver *s) { return !s || s->nranks == 1 ? 0 : (s->p2p_on ? 2 : 1); }
 
