@@ -51,6 +51,9 @@
 #ifndef RS_WARPS
 #define RS_WARPS 4  // warps per block (independent of each other; adjacent strips, so a block reads 4 x 512 contiguous bytes per row)
 #endif
+#ifndef RS_VC_BLOCKS
+#define RS_VC_BLOCKS 2 // resident blocks per SM the V-cycle variant is compiled for
+#endif
 #define RS_BLOCKS_PER_SM (12 / RS_WARPS) // 12 warps per SM fit (shared memory: 17 KB per warp)
 #ifndef RS_PAD
 #define RS_PAD 0    // 1: one double of padding after every 16 columns, rows copied with 8-byte cp.async; 0: dense rows, 16-byte cp.async
@@ -106,7 +109,7 @@ struct RsCoarse {
     int P;
 };
 template <int POW2, int VC>
-__global__ void __launch_bounds__(32 * RS_WARPS, RS_BLOCKS_PER_SM)
+__global__ void __launch_bounds__(32 * RS_WARPS, VC ? RS_VC_BLOCKS : RS_BLOCKS_PER_SM) // VC: 2 blocks per SM keep its extra operands out of local memory
     k_rbgs_stream(Geom g, const double *__restrict__ pin, double *__restrict__ pout, const double *__restrict__ rhs,
                   Scalars *sc, double *partials, double tol, int RY, int nstrips, int finish, RsCoarse cz, WaitArgs hw) { pdl_begin();
     // Strip of rows this block works on.  The first strip goes to the LAST blocks of the grid: on a row slab the strips at
