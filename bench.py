@@ -276,6 +276,14 @@ class Ctx:
         return float(t.item())
 
 
+def owned_rows(r, N, nrows):
+    """Row ranges (local, inside a slab's host arrays u / v / p) that slab r of N owns: its cell rows, the shared v face
+    row at its bottom, and the domain's ghost rows on the end slabs.  Same rule as tests/slab_worker.py."""
+    b, t = r == 0, r == N - 1
+    return {"u": (0 if b else 1, nrows + 2 if t else nrows + 1), "v": (0 if b else 1, nrows + 3 if t else nrows + 1),
+            "p": (0 if b else 1, nrows + 2 if t else nrows + 1)}
+
+
 def slab_parity(ctx, name, s, reset, bc, Re, CFL, pp, steps=2):
     """N row slabs against ONE GPU running the same global grid: `steps` steps from the reset state on both, then every
     rank compares the rows it owns (domain ghost rows included on the end slabs) with the same rows of the 1-GPU State,
@@ -291,10 +299,8 @@ def slab_parity(ctx, name, s, reset, bc, Re, CFL, pp, steps=2):
     n, r0 = s.nrows, s.row0
     bottom, top = ctx.rank == 0, ctx.rank == ctx.N - 1
 
-    def owned(r, nrows):  # row ranges (local, within the slab's host arrays) a rank owns; same rule as tests/slab_worker.py
-        b, t = r == 0, r == ctx.N - 1
-        return {"u": (0 if b else 1, nrows + 2 if t else nrows + 1), "v": (0 if b else 1, nrows + 3 if t else nrows + 1),
-                "p": (0 if b else 1, nrows + 2 if t else nrows + 1)}
+    def owned(r, nrows):
+        return owned_rows(r, ctx.N, nrows)
 
     ref_parts = {}
     ref_hist = None
