@@ -635,19 +635,21 @@ void launch_fused(cfd_b200_solver *s, double tol, int ntx, int nty, int finish, 
 // `sm_count` SMs, or 0 when the streaming smoother would leave SMs empty and the tile kernel is the better choice.
 int stream_strip_rows(int nx, int nrows, int sm_count, int *gx_out, int *nstrips_out) {
     const int nstrips = cdiv(nx + 1, RS_OUT), gx = cdiv(nstrips, RS_WARPS);
-    // Rows per strip: 16 m + 1, so that the RY + 15 steps of a strip are whole turns of the 16-row ring.  Tall strips
-    // waste fewer steps on the pipeline fill, short ones give more blocks.  Cost model fitted on B200 (8192x1024 ...
-    // 16384x4096, scripts/strip_sweep.py): a block costs RY + 15 steps + ~12 steps of fixed overhead; the blocks run
-    // in rounds of RS_BLOCKS_PER_SM per SM, a full round at unit cost per step and a partly filled last round at
-    // 0.6 + 0.4 x fill (fewer resident warps hide less latency).  It picks the measured optimum in every case tried:
-    // 8192^2 -> 257, 8192x4096 -> 129, 8192x2048 / 4096^2 -> 257, 8192x1024 -> 129, 2048^2 -> 65.
+    // Rows per strip.  Tall strips waste fewer steps on the pipeline fill, short ones give more blocks.  Cost model fitted on
+    // B200 with the round-2 kernel (scripts/strip_sweep.py, 8192x1024 ... 16384x4096): a block costs its steps -- whole turns
+    // of the 16-row ring, 16 * ceil((RY + 15) / 16) -- plus ~12 steps of fixed overhead; the blocks run in rounds of
+    // RS_BLOCKS_PER_SM per SM, a full round at unit cost per step and a partly filled last round at 0.5 + 0.5 x fill (fewer
+    // resident warps hide less latency, but each runs faster).  It picks the measured optimum in every case tried:
+    // 8192^2 and 16384x4096 -> 257, 8192x4096, 8192x2048 and 4096^2 -> 193, 8192x1024 -> 97, 2048^2 -> 49.
     int RY = 257;
     const double slots = (double)RS_BLOCKS_PER_SM * sm_count;
     double best = 1e300;
-    for (int ry = 257; ry >= 33; ry = (ry - 1) / 2 + 1) {
+    static const int cand[] = {257, 193, 129, 97, 65, 49, 33};
+    for (int ry : cand) {
         const double blocks = (double)gx * cdiv(nrows, ry);
         const double full = std::floor(blocks / slots), rem = blocks - full * slots;
-        const double cost = (ry + 27) * (full + (rem > 0 ? 0.6 + 0.4 * rem / slots : 0.0));
+        const double steps = 16.0 * cdiv(ry + 15, 16) + 12.0;
+        const double cost = steps * (full + (rem > 0 ? 0.5 + 0.5 * rem / slots : 0.0));
         if (cost < best) best = cost, RY = ry;
     }
     if (gx_out) *gx_out = gx;

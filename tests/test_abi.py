@@ -91,11 +91,11 @@ def test_argument_validation_happens_before_the_device_is_touched():
 
 def test_smoother_strip_model_picks_the_measured_optima():
     """Host-only arithmetic: the strip height of the streaming smoother against the B200 sweep in
-    profiles/r01_experiments.md (148 SMs); 0 = grid too small, the tile smoother runs."""
+    profiles/r02_strip_sweep.txt (148 SMs, round-2 kernel); 0 = grid too small, the tile smoother runs."""
     import importlib
     L = importlib.import_module("macos-cfd_b200").load_library()
-    want = {(8192, 8192): 257, (8192, 4096): 129, (8192, 2048): 257, (4096, 4096): 257, (8192, 1024): 129,
-            (2048, 2048): 65, (16384, 4096): 257, (1024, 1024): 0, (512, 256): 0}
+    want = {(8192, 8192): 257, (8192, 4096): 193, (8192, 2048): 193, (4096, 4096): 193, (8192, 1024): 97,
+            (2048, 2048): 49, (16384, 4096): 257, (1024, 1024): 0, (512, 256): 0}
     for (nx, ny), ry in want.items():
         assert L.cfd_b200_smoother_strip_for(nx, ny, 148) == ry, (nx, ny)
     assert L.cfd_b200_smoother_strip_for(2, 2, 148) < 0  # argument validation
