@@ -43,6 +43,8 @@ WORKLOADS = {
     "shear_pcg_4096": ("shear", "pcg", 4096, 4096, 1.0, 1.0, 2, 1e-6, 200, 2),
     "jet_mg_1024": ("jet", "mg", 1024, 1024, 1.0, 1.0, 2, 1e-6, 200, 1),
     "lid_pcg_512x256": ("lid", "pcg", 512, 256, 2.0, 1.0, 2, 1e-8, 200, 0),
+    # one slab of the 8-GPU strong-scaling case per GPU (tuning: what a 1024-row slab costs)
+    "lid_mg_8192x1024": ("lid", "mg", 8192, 1024, 1.0, 0.125, 2, 1e-6, 200, 3),
     # STRONG scaling: the global grid is fixed and split into N row slabs (BASELINE configs[3], configs[2])
     "lid_mg_8192_strong": ("lid", "mg", 8192, 8192, 1.0, 1.0, 2, 1e-6, 200, 3),
     "shear_pcg_4096_strong": ("shear", "pcg", 4096, 4096, 1.0, 1.0, 2, 1e-6, 200, 2),
@@ -427,22 +429,23 @@ def run_workload(ctx, name, steps, warmup, variant=1, want_e2e=True, want_parity
         config["timing"] += f" (chunk = {chunk} steps)"
         s.reset()
         s.sync()
-    total_ms = 0.0
+    # Everything is enqueued without a host round trip in between: one CUDA-event pair per chunk (or, on L2-resident grids,
+    # per step, with the L2 flush in front of it and outside it); the device-side resets between chunks sit outside the
+    # pairs too.  barrier + synchronize bracket the whole region; the time is the sum of the pairs, max over ranks.
+    pairs = []
+    ctx.barrier()
     if flush is None:
         left = steps
         while left > 0:
             n = min(chunk, left)
             if chunk < steps:
                 s.reset()
-            ctx.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             for _ in range(n):
                 s.step_async(bc, Re, CFL, pp)
             e1.record(stream)
-            info = s.sync()
-            ctx.barrier()
-            total_ms += ctx.reduce(e0.elapsed_time(e1))
+            pairs.append((e0, e1))
             left -= n
     else:
         for i in range(steps):
@@ -454,9 +457,10 @@ def run_workload(ctx, name, steps, warmup, variant=1, want_e2e=True, want_parity
             e0.record(stream)
             s.step_async(bc, Re, CFL, pp)
             e1.record(stream)
-            info = s.sync()
-            ctx.barrier()
-            total_ms += ctx.reduce(e0.elapsed_time(e1))
+            pairs.append((e0, e1))
+    info = s.sync()
+    ctx.barrier()
+    total_ms = ctx.reduce(sum(a.elapsed_time(b) for a, b in pairs))
     launches = s.launch_count - l0
     if N > 1:  # where this rank polled for its neighbours during the timed steps (+ the probe), per step
         config["peer_wait_us_per_step_rank0"] = {k: [round(v[0] / max(steps, 1), 2), v[1]] for k, v in s.wait_stats().items()}
