@@ -36,7 +36,8 @@ struct Session {
 };
 
 namespace {
-std::map<const Grid *, Session *> g_sessions;
+// never destroyed: host arrays with static storage may be freed (Field2D::free -> forget_host_array) after this file's statics
+std::map<const Grid *, Session *> &g_sessions = *new std::map<const Grid *, Session *>;
 Coherence g_coherence = Coherence::Eager;
 bool g_coherence_set = false;
 int g_device = -1;
@@ -119,6 +120,14 @@ static Session *find_by_state(const double *u, const double *v) {
         if (kv.second->host_u == u && kv.second->host_v == v) return kv.second;
     return nullptr;
 }
+// Lazy mode recognises "the same State as last step" by the addresses of its u / v arrays.  When such an array is freed, a
+// later State may get the same address: the Session must not take it for the one it mirrors.
+void forget_host_array(const void *data) {
+    for (auto &kv : g_sessions) {
+        Session *s = kv.second;
+        if (s->host_u == data || s->host_v == data) s->host_u = s->host_v = nullptr, s->host_dirty = true, s->host_stale = false;
+    }
+}
 void mark_host_dirty(const State &st) {
     if (Session *s = find_by_state(st.u.data, st.v.data)) s->host_dirty = true, s->host_stale = false;
 }
@@ -143,12 +152,25 @@ PressureSolver::~PressureSolver() { b200::release(session_); }
 
 double PressureSolver::solve(Field2D<double> &p, const Field2D<double> &rhs, const PressureParams &params) {
     cfd_b200_solver *h = session_->h;
+    // The Session is shared with the TimeIntegrator of the same Grid, and this stand-alone solve borrows its device p and
+    // rhs.  In lazy mode the device State may be ahead of the host: keep its p / rhs aside and put them back afterwards.
+    const bool borrow = session_->host_stale;
+    Field2D<double> keep_p, keep_rhs;
+    if (borrow) {
+        keep_p.allocate(p.nx, p.ny, p.pitch, p.ngx, p.ngy);
+        keep_rhs.allocate(p.nx, p.ny, p.pitch, p.ngx, p.ngy);
+        check(cfd_b200_download(h, nullptr, nullptr, keep_p.data, keep_rhs.data), "cfd_b200_download");
+    }
     check(cfd_b200_upload(h, nullptr, nullptr, p.data), "cfd_b200_upload");
     check(cfd_b200_upload_rhs(h, rhs.data), "cfd_b200_upload_rhs");
     cfd_b200_params pp = b200::to_c(params);
     double res = 0.0;
     check(cfd_b200_pressure_solve(h, &pp, &res, &last_iters_), "cfd_b200_pressure_solve");
     check(cfd_b200_download(h, nullptr, nullptr, p.data, nullptr), "cfd_b200_download");
+    if (borrow) {
+        check(cfd_b200_upload(h, nullptr, nullptr, keep_p.data), "cfd_b200_upload");
+        check(cfd_b200_upload_rhs(h, keep_rhs.data), "cfd_b200_upload_rhs");
+    }
     if (res == 1e9 && !warned_nan_) { // pressure.cpp:124-127, :233-236
         std::fprintf(stderr, "Non-finite pressure residual\n");
         warned_nan_ = true;

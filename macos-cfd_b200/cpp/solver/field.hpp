@@ -12,6 +12,7 @@
 
 extern "C" void *cfd_b200_host_alloc(size_t bytes); // pinned, 64-byte aligned; NULL on failure
 extern "C" void cfd_b200_host_free(void *p);
+namespace b200 { void forget_host_array(const void *data); } // a host array goes away: no Session may keep mirroring it
 
 template <typename T> struct Field2D {
     int nx = 0, ny = 0, pitch = 0, ngx = 0, ngy = 0;
@@ -43,7 +44,7 @@ template <typename T> struct Field2D {
     }
 
     void free() {
-        if (data) cfd_b200_host_free(data);
+        if (data) b200::forget_host_array(data), cfd_b200_host_free(data);
         data = nullptr;
         nx = ny = pitch = ngx = ngy = 0;
     }

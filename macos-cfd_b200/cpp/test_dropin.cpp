@@ -97,6 +97,25 @@ int main(int argc, char **argv) {
         std::vector<unsigned char> rgb;
         b200::render_rgb(grid, st, ScalarField::Speed, /*Turbo*/ 4, 0.0f, 1.0f, false, 1.0f, rgb);
         std::ofstream(dir + "/rgb.bin", std::ios::binary).write(reinterpret_cast<const char *>(rgb.data()), static_cast<std::streamsize>(rgb.size()));
+
+        // lazy coherence: the State lives on the device.  A stand-alone PressureSolver::solve on other arrays (it shares the
+        // Grid's device session) must not disturb it, and a new State that happens to get a freed State's addresses must
+        // not be taken for the old one.
+        b200::set_coherence(b200::Coherence::Lazy);
+        for (int round = 0; round < 2; ++round) {
+            State lz;
+            lz.u.allocate(grid.u_nx(), grid.ny, grid.u_pitch(), grid.ngx, grid.ngy);
+            lz.v.allocate(grid.nx, grid.v_ny(), grid.v_pitch(), grid.ngx, grid.ngy);
+            lz.p.allocate(grid.nx, grid.ny, grid.p_pitch(), grid.ngx, grid.ngy);
+            lz.rhs.allocate(grid.nx, grid.ny, grid.p_pitch(), grid.ngx, grid.ngy);
+            integ.clear_work();
+            for (int step = 0; step < 6; ++step) {
+                integ.step(lz, bc, 1000.0, 0.1, pressure, pp, res, 0.0005);
+                if (step == 2) solver2.solve(p2, rhs2, pcg); // device p / rhs of the stepped State are ahead of the host here
+            }
+            b200::sync_to_host(lz);
+            dump(dir + (round ? "/lazy2_u.bin" : "/lazy_u.bin"), lz.u), dump(dir + (round ? "/lazy2_p.bin" : "/lazy_p.bin"), lz.p);
+        } // round 1 allocates its State where round 0's was freed
     } catch (const std::exception &e) {
         std::fprintf(stderr, "test_dropin: %s\n", e.what());
         return 1;

@@ -342,7 +342,15 @@ void p2p_unmap(cfd_b200_solver *s) {
     cudaGetLastError();
 }
 
+int p2p_setup_impl(cfd_b200_solver *s, P2PInfo *&d_all);
 int p2p_setup(cfd_b200_solver *s) {
+    P2PInfo *d_all = nullptr;
+    const int rc = p2p_setup_impl(s, d_all);
+    if (d_all) cudaFree(d_all);
+    if (rc) p2p_unmap(s), s->p2p_on = false; // nothing stays mapped behind a failed bootstrap
+    return rc;
+}
+int p2p_setup_impl(cfd_b200_solver *s, P2PInfo *&d_all) {
     static const int env = getenv("CFD_B200_P2P") ? atoi(getenv("CFD_B200_P2P")) : 1;
     NcclApi &nc = nccl_api();
     const int R = s->nranks;
@@ -353,7 +361,6 @@ int p2p_setup(cfd_b200_solver *s) {
               cudaIpcGetMemHandle(&mine.handle, s->arena) == cudaSuccess;
     cudaGetLastError();
     // all-gather of the descriptors (bytes) on the solver's stream: ordered after the arena memset and the magic
-    P2PInfo *d_all = nullptr;
     CU(cudaMalloc(&d_all, (size_t)R * sizeof(P2PInfo)));
     CU(cudaMemcpyAsync(d_all + s->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, s->stream));
     NCCLCHK(nc.AllGather(d_all + s->rank, d_all, sizeof(P2PInfo), ncclInt8, s->comm, s->stream));
@@ -381,7 +388,6 @@ int p2p_setup(cfd_b200_solver *s) {
     NCCLCHK(nc.AllReduce(s->gathered, s->gathered, 1, ncclDouble, ncclMin, s->comm, s->stream));
     CU(cudaMemcpyAsync(&okd, s->gathered, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
-    cudaFree(d_all);
     s->p2p_on = okd > 0.5;
     if (!s->p2p_on) p2p_unmap(s);
     s->peer_arena[s->rank] = s->arena;

@@ -163,6 +163,9 @@ struct RedArgs {
 #define P2P_RED_THREADS 256
 
 __global__ void __launch_bounds__(P2P_RED_THREADS) k_p2p_reduce(RedArgs a, Scalars *sc) { pdl_begin();
+    // a solver that has converged keeps enqueuing its iterations (no host round trip): their reductions, and the rows that
+    // ride on them, are skipped -- by every rank alike, `done` comes from totals that are bit-identical everywhere
+    if ((a.kind == RED_PCG1 || a.kind == RED_PCG2 || a.kind == RED_RBGS || a.kind == RED_VC) && sc->done) return;
     const int t = threadIdx.x, par = (int)(a.epoch & 1ull);
     P2PBlock *me = a.blk[a.rank];
     double v0, v1, v2 = 0.0, v3 = 0.0, v4 = 0.0;

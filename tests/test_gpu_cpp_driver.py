@@ -177,3 +177,10 @@ def test_eager_drop_in_like_the_gui_loop(exe, port, tmp_path):
     assert abs(got[4] - vort[3]) <= 1e-12 * abs(vort[3]) + 1e-15 and abs(got[5] - vort[4]) <= 1e-10 * vort[4]
     rgb = port.render_rgb(nx, ny, Lx, Ly, su, sv, sim.p, cfdo.FIELDS["speed"], 4)
     assert np.array_equal(np.fromfile(tmp_path / "rgb.bin", dtype=np.uint8).reshape(ny, nx, 3), rgb)
+    # lazy coherence: 6 steps with a stand-alone PressureSolver::solve on other arrays in the middle, twice (the second
+    # State reuses the first one's freed addresses) -- both must equal 6 undisturbed steps from the zero state
+    sim2 = cfdo.Sim(port, nx, ny, Lx, Ly)
+    for _ in range(6):
+        sim2.step(bc, 1000.0, 0.1, cfdo.make_params("mg", vcycles=2), dt_override=0.0005)
+    for tag in ("lazy", "lazy2"):
+        assert same(load(f"{tag}_u.bin", "u"), sim2.u) and same(load(f"{tag}_p.bin", "p"), sim2.p), tag
