@@ -73,6 +73,22 @@ struct cfd_b200_solver {
     cudaStream_t stream = nullptr;
     cudaStream_t comm_stream = nullptr; // row slabs: the one-way sends run here, next to the solver's kernels
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // Captured CUDA graph of a steady-state step (single GPU, reference-mode mg): replayed while the step's arguments, the
+    // launch sequence (cached CFL maxima, same BC) and the roles of p / p_alt stay what they were at capture time.  Two slots:
+    // an odd number of smooth() calls per step swaps p and p_alt, so consecutive steps alternate between two graphs.
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+        cfd_b200_bc bc{};
+        cfd_b200_params pp{};
+        double Re = 0, CFL = 0, dt_override = 0;
+        int variant = 0, rb_strip = 0;
+        double *p = nullptr;
+        long long launches = 0;
+        bool swaps_p = false;
+        int last_smoother = 0;
+    } step_graph[2];
+    int graph_mode = -1;                // -1 unread, 0 off (CFD_B200_GRAPH=0 or a failed capture), 1 on
+    int graph_seen = 0;                 // consecutive eligible steps seen with the same key (capture on the second)
     bool comm_pending = false;          // a send was enqueued on comm_stream since the last join
     bool defer_rbgs = false;            // the residual sum of the step's last smooth() is completed by the reduction that ends the step
     double defer_tol = 0.0;
@@ -1435,6 +1451,8 @@ void cfd_b200_destroy(cfd_b200_solver *s) {
     if (s->h_sc) cudaFreeHost(s->h_sc);
     for (int i = 0; i < ST_COUNT; ++i)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    for (auto &g : s->step_graph)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
@@ -1515,6 +1533,57 @@ int cfd_b200_step_async(cfd_b200_solver *s, const cfd_b200_bc *bc, double Re, do
     if (!s || !bc || !pp) return fail(CFD_B200_EINVAL, "NULL argument");
     if (pp->solver != CFD_B200_SOLVER_PCG && pp->solver != CFD_B200_SOLVER_MG) return fail(CFD_B200_EINVAL, "bad solver type");
     CU(cudaSetDevice(s->device));
+    // ---- steady-state steps of a single-GPU handle go through a captured graph (launch-bound small grids gain most)
+    if (s->graph_mode < 0) s->graph_mode = getenv("CFD_B200_GRAPH") ? atoi(getenv("CFD_B200_GRAPH")) : 1;
+    const bool eligible = s->graph_mode == 1 && s->nranks == 1 && !s->profiling && s->variant == 1 && s->cfl_cached &&
+                          pp->solver == CFD_B200_SOLVER_MG && pp->mg_mode == CFD_B200_MG_REFERENCE && pp->vcycles >= 1 &&
+                          bc_equal(s->last_bc, *bc);
+    if (!eligible) {
+        s->graph_seen = 0;
+        return enqueue_step(s, bc, Re, CFL, pp, dt_override);
+    }
+    auto matches = [&](const cfd_b200_solver::StepGraph &g) {
+        return g.exec && g.p == s->p && bc_equal(g.bc, *bc) && g.Re == Re && g.CFL == CFL && g.dt_override == dt_override &&
+               g.variant == s->variant && g.rb_strip == s->rb_strip && g.pp.vcycles == pp->vcycles && g.pp.tol == pp->tol &&
+               g.pp.mg_levels == pp->mg_levels && g.pp.rbgs_sweeps == pp->rbgs_sweeps;
+    };
+    for (auto &g : s->step_graph)
+        if (matches(g)) {
+            CU(cudaGraphLaunch(g.exec, s->stream));
+            s->launches += g.launches;
+            if (g.swaps_p) { double *t = s->p; s->p = s->p_alt; s->p_alt = t; }
+            s->last_smoother = g.last_smoother;
+            s->last_bc_step = *bc;
+            s->ev_valid = false;
+            return 0;
+        }
+    if (++s->graph_seen < 2) return enqueue_step(s, bc, Re, CFL, pp, dt_override); // first: run plainly (lazy initialisations)
+    // capture this step; if anything in it cannot be captured, graphs stay off for this handle
+    cfd_b200_solver::StepGraph *slot = s->step_graph[0].exec && s->step_graph[0].p != s->p ? &s->step_graph[1] : &s->step_graph[0];
+    if (slot->exec) cudaGraphExecDestroy(slot->exec), slot->exec = nullptr;
+    double *const p0 = s->p, *const palt0 = s->p_alt;
+    const long long l0 = s->launches;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        s->graph_mode = 0;
+        return enqueue_step(s, bc, Re, CFL, pp, dt_override);
+    }
+    const int rc = enqueue_step(s, bc, Re, CFL, pp, dt_override);
+    const cudaError_t ec = cudaStreamEndCapture(s->stream, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (rc == 0 && ec == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+        cudaGraphDestroy(graph);
+        slot->exec = exec, slot->bc = *bc, slot->pp = *pp, slot->Re = Re, slot->CFL = CFL, slot->dt_override = dt_override;
+        slot->variant = s->variant, slot->rb_strip = s->rb_strip, slot->p = p0, slot->launches = s->launches - l0;
+        slot->swaps_p = s->p != p0, slot->last_smoother = s->last_smoother;
+        CU(cudaGraphLaunch(exec, s->stream)); // the capture recorded the step, it did not run it
+        return 0;
+    }
+    // not capturable: nothing was executed, put the host-side state back and run the step the plain way
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    s->p = p0, s->p_alt = palt0, s->launches = l0, s->graph_mode = 0;
     return enqueue_step(s, bc, Re, CFL, pp, dt_override);
 }
 
