@@ -210,3 +210,44 @@ def test_mg_is_fine_grid_rbgs_only(port):
     port.pressure_solve(nx, ny, Lx, Ly, a, rhs, cfdo.make_params("mg", vcycles=2, mg_levels=3, rbgs_sweeps=2))
     port.pressure_solve(nx, ny, Lx, Ly, b, rhs, cfdo.make_params("mg", vcycles=2, mg_levels=7, rbgs_sweeps=9))
     assert same(a, b)
+
+
+def test_tvd_debug_log_of_the_reference_is_unreachable_for_finite_fields(ref, tmp_path):
+    """advection.cpp:19-27 prints "TVD max overshoot before clipping" when a limited face state leaves the interval of its
+    three samples by more than 1e-10.  For finite samples it cannot: c + minmod(c - m1, p1 - c) / 2 lies between c and p1,
+    overflowing differences included (minmod then returns the finite one, or 0 when the signs differ).  TimeIntegrator::step
+    only ever advects sanitised, i.e. finite, fields, so inside a step the line is dead -- which is why the B200 path
+    evaluates the clip only on its slow path and has no overshoot log.  Evidence: the reference's own code with
+    tvd_debug = true on fields mixing ordinary, tiny, huge and overflowing values.  (Non-finite caller arrays handed to the
+    free functions advect_u / advect_v do print "inf"; checked last, to show the capture works.)"""
+    import ctypes
+    flag = ctypes.c_bool.in_dll(ref.L, "tvd_debug")
+    nx, ny, Lx, Ly = 24, 16, 1.5, 1.0
+    sh = cfdo.shapes(nx, ny)
+    rng = np.random.default_rng(5)
+    pool = np.array([0.0, -0.0, 1.0, -1.0, 1e-300, 3.0, 1e300, -1e300, 1.0e308, 1.7e308, -1.7e308])
+
+    def run(u, v):
+        log = tmp_path / "stderr.txt"
+        fd = os.open(str(log), os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+        saved = os.dup(2)
+        os.dup2(fd, 2)
+        flag.value = True
+        try:
+            du, dv = np.zeros(sh["u"]), np.zeros(sh["v"])
+            ref.advect_u(nx, ny, Lx, Ly, u, v, du)
+            ref.advect_v(nx, ny, Lx, Ly, u, v, dv)
+        finally:
+            flag.value = False
+            os.dup2(saved, 2)
+            os.close(saved)
+            os.close(fd)
+        return log.read_text()
+
+    for trial in range(60):
+        u, v = rng.choice(pool, size=sh["u"]), rng.choice(pool, size=sh["v"])
+        if trial % 2:
+            u, v = u * rng.uniform(0.5, 1.0, sh["u"]), v * rng.uniform(0.5, 1.0, sh["v"])
+        assert run(u, v) == "", trial
+    wild = np.r_[pool, [np.inf, -np.inf, np.inf, -np.inf]]
+    assert "TVD max overshoot before clipping: inf" in run(rng.choice(wild, size=sh["u"]), rng.choice(wild, size=sh["v"]))
