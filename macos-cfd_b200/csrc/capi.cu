@@ -115,6 +115,7 @@ struct cfd_b200_solver {
     unsigned long long halo_epoch = 0, red_epoch = 0;
     unsigned long long p2p_timeout_ns = 20000000000ull;
     double *gathered = nullptr; // 4 doubles per rank (k_slab_pack / k_slab_unpack)
+    double *bt_far = nullptr;   // both bottom/top Periodic: 5 rows received from the slab at the other end of the domain
     unsigned sent_since_barrier = 0;      // bit fi: a one-way send wrote the neighbours' halo rows of arena field fi since the last reduction
     unsigned long long ep_uv = 0;         // one-way send that delivers the u, v (and p) halo rows for the next step; 0 = none pending
     bool p_halo_valid = false;            // the 5 halo rows of p the smoother reads are current (sent at the end of the last step)
@@ -206,11 +207,29 @@ void stage_mark(cfd_b200_solver *s, int st) {
 }
 
 // apply_bc_u / apply_bc_v / apply_bc_p in the reference's pass order (left/right, then bottom/top)
+void join_comm(cfd_b200_solver *s);
 void enqueue_bc(cfd_b200_solver *s, const BcD &bc, double *u, double *v, double *p, int sanitize, int halo = 1) {
     const Geom &g = s->g;
     const int nf = p ? 3 : 2; // blockIdx.y = field (u, v, p)
     LAUNCH(s, k_bc_lr, dim3(cdiv(g.ny + 5, 128), nf), 128, g, bc, u, v, p, sanitize, s->d_sc, halo);
-    if (g.bottom || g.top) LAUNCH(s, k_bc_bt, dim3(cdiv(g.nx + 3, 128), nf), 128, g, bc, u, v, p, sanitize, s->d_sc);
+    const double *far = nullptr;
+    if (s->nranks > 1 && bc.bottom.type == BC_PERIODIC && bc.top.type == BC_PERIODIC && (g.bottom || g.top)) {
+        // both bottom/top Periodic across slabs (bc.cpp:171-183, :318-330, :361-379): the pass swaps the boundary rows of the
+        // two ends of the domain, which live on the first and the last slab.  They trade those rows (as left by the left/right
+        // pass above) in front of the kernel: u 2 rows, v 2 rows, p 1 row.
+        NcclApi &nc = nccl_api();
+        join_comm(s);
+        const int peer = g.bottom ? s->nranks - 1 : 0;
+        const size_t P = g.P;
+        auto row = [&](double *f, int jj) { return f + (size_t)(jj + CFD_YOFF) * P; };
+        nc.GroupStart();
+        if (u) nc.Send(row(u, g.bottom ? 1 : g.ny - 1), 2 * P, ncclDouble, peer, s->comm, s->stream), nc.Recv(s->bt_far, 2 * P, ncclDouble, peer, s->comm, s->stream);
+        if (v) nc.Send(row(v, g.bottom ? 1 : g.ny), 2 * P, ncclDouble, peer, s->comm, s->stream), nc.Recv(s->bt_far + 2 * P, 2 * P, ncclDouble, peer, s->comm, s->stream);
+        if (p) nc.Send(row(p, g.bottom ? 1 : g.ny), P, ncclDouble, peer, s->comm, s->stream), nc.Recv(s->bt_far + 4 * P, P, ncclDouble, peer, s->comm, s->stream);
+        nc.GroupEnd();
+        far = s->bt_far;
+    }
+    if (g.bottom || g.top) LAUNCH(s, k_bc_bt, dim3(cdiv(g.nx + 3, 128), nf), 128, g, bc, u, v, p, sanitize, s->d_sc, far);
 }
 
 int reduce_fin(cfd_b200_solver *s, int kind, double tol, int max_iters, double *halo = nullptr, int rows = 0, int dirs = 0);
@@ -1138,9 +1157,6 @@ int enqueue_step(cfd_b200_solver *s, const cfd_b200_bc *bc_in, double Re, double
                  double dt_override) {
     const Geom &g = s->g;
     const BcD bc = to_bcd(bc_in);
-    const bool both_bt = bc.bottom.type == BC_PERIODIC && bc.top.type == BC_PERIODIC;
-    if (both_bt && s->nranks > 1)
-        return fail(CFD_B200_EUNSUPPORTED, "bottom/top Periodic is not supported across row slabs");
     const double invRe = 1.0 / Re; // "1.0 / Re" at time_integrator.cpp:76
     if (!bc_equal(s->last_bc, *bc_in) || s->variant == 0) s->cfl_cached = false;
     s->last_bc = *bc_in;
@@ -1406,6 +1422,7 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
             ncclResult_t r = nccl_api().CommInitRank(&s->comm, nranks, id, rank);
             if (r != ncclSuccess) { rc = fail(CFD_B200_ECOMM, "ncclCommInitRank: %s", nccl_api().GetErrorString(r)); break; }
             if (cudaMalloc(&s->gathered, 4 * nranks * sizeof(double)) != cudaSuccess) { rc = fail(CFD_B200_ENOMEM, "gather buffer"); break; }
+            if (cudaMalloc(&s->bt_far, 5 * (size_t)s->g.P * sizeof(double)) != cudaSuccess) { rc = fail(CFD_B200_ENOMEM, "periodic rows buffer"); break; }
             if ((rc = p2p_setup(s)) != 0) break;
         }
     } while (0);
@@ -1435,6 +1452,7 @@ void cfd_b200_destroy(cfd_b200_solver *s) {
     p2p_teardown(s);
     if (s->comm) nccl_api().CommDestroy(s->comm);
     if (s->gathered) cudaFree(s->gathered);
+    if (s->bt_far) cudaFree(s->bt_far);
     if (s->coop_xrows) cudaFree(s->coop_xrows);
     if (s->coop_slots) cudaFree(s->coop_slots);
     for (int l = 1; l < s->mg_nlev; ++l) {

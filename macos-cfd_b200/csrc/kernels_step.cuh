@@ -91,9 +91,30 @@ __global__ void k_bc_lr(Geom g, BcD bc, double *u, double *v, double *p, int san
 }
 
 // bottom/top pass on one column; col points at raw row 0 of that column; rT = top boundary line.
+// Both sides Periodic (bc.cpp:171-183 / :318-330) swaps the boundary rows on every call: ghost and boundary row of either
+// end take the pre-pass values of the other end.  On row slabs the two ends live on the first and the last slab: `far`
+// then points at this column of the two rows the OTHER end holds (far[0], far[farP]: its boundary-side pair in the order
+// inner, boundary for the top end / boundary, inner for the bottom end), exchanged in front of this kernel.
 __device__ __forceinline__ void bc_col(double *col, size_t P, int rT, bool both, bool do_b, bool do_t, int btype,
-                                       double bmov, double binf, int ttype, double tmov, double tinf) {
+                                       double bmov, double binf, int ttype, double tmov, double tinf,
+                                       const double *far = nullptr, size_t farP = 0) {
     double val;
+    if (both) {
+        if (do_b && do_t) {
+            double bb = col[P], bi = col[2 * P], tb = col[(size_t)rT * P], ti = col[(size_t)(rT - 1) * P];
+            col[0] = ti;
+            col[P] = tb;
+            col[(size_t)rT * P] = bb;
+            col[(size_t)(rT + 1) * P] = bi;
+        } else if (do_b) { // first slab: far = the last slab's rows rT-1, rT
+            col[0] = far[0];
+            col[P] = far[farP];
+        } else if (do_t) { // last slab: far = the first slab's rows 1, 2
+            col[(size_t)rT * P] = far[0];
+            col[(size_t)(rT + 1) * P] = far[farP];
+        }
+        return;
+    }
     if (do_b && side_value(btype, bmov, binf, col[2 * P], val)) {
         col[P] = val;
         col[0] = val;
@@ -102,21 +123,17 @@ __device__ __forceinline__ void bc_col(double *col, size_t P, int rT, bool both,
         col[(size_t)rT * P] = val;
         col[(size_t)(rT + 1) * P] = val;
     }
-    if (both) { // bc.cpp:171-183 / :318-330 (single-slab handles only; rejected on the host otherwise)
-        double bb = col[P], bi = col[2 * P], tb = col[(size_t)rT * P], ti = col[(size_t)(rT - 1) * P];
-        col[0] = ti;
-        col[P] = tb;
-        col[(size_t)rT * P] = bb;
-        col[(size_t)(rT + 1) * P] = bi;
-    }
 }
 
-__global__ void k_bc_bt(Geom g, BcD bc, double *u, double *v, double *p, int sanitize, Scalars *sc) { pdl_begin();
+// far (row slabs with both bottom/top Periodic, else NULL): 5 rows of pitch g.P received from the slab at the other end of
+// the domain -- u (2 rows), v (2 rows), p (1 row), see bc_col.
+__global__ void k_bc_bt(Geom g, BcD bc, double *u, double *v, double *p, int sanitize, Scalars *sc, const double *far) { pdl_begin();
     int ii = blockIdx.x * blockDim.x + threadIdx.x; // raw column 0 .. nx+2
     const int f = blockIdx.y;                        // field, as in k_bc_lr
     int flag = 0;
     bool both = bc.bottom.type == BC_PERIODIC && bc.top.type == BC_PERIODIC;
     const size_t P = g.P;
+    const double *farc = far ? far + CFD_XOFF + ii : nullptr; // this column in the received rows
     if (f == 0 && u && ii <= g.nx + 2) {
         double *col = u + gidx(g, ii, 0);
         if (sanitize) { // ghost rows (true domain ghosts only)
@@ -125,7 +142,7 @@ __global__ void k_bc_bt(Geom g, BcD bc, double *u, double *v, double *p, int san
         }
         if (ii >= 1 && ii <= g.nx + 1) // apply_bc_u columns, bc.cpp:111-183: tangential
             bc_col(col, P, g.ny, both, g.bottom, g.top, bc.bottom.type, bc.bottom.moving, bc.bottom.inflow_u,
-                   bc.top.type, bc.top.moving, bc.top.inflow_u);
+                   bc.top.type, bc.top.moving, bc.top.inflow_u, farc, P);
     }
     if (f == 1 && v && ii <= g.nx + 1) {
         double *col = v + gidx(g, ii, 0);
@@ -135,7 +152,7 @@ __global__ void k_bc_bt(Geom g, BcD bc, double *u, double *v, double *p, int san
         }
         if (ii >= 1 && ii <= g.nx) // apply_bc_v columns, bc.cpp:268-330: normal (Wall and Moving give 0)
             bc_col(col, P, g.ny + 1, both, g.bottom, g.top, bc.bottom.type, 0.0, bc.bottom.inflow_v, bc.top.type,
-                   0.0, bc.top.inflow_v);
+                   0.0, bc.top.inflow_v, farc ? farc + 2 * P : nullptr, P);
     }
     if (f == 2 && p && ii <= g.nx + 1) {
         double *col = p + gidx(g, ii, 0);
@@ -144,7 +161,9 @@ __global__ void k_bc_bt(Geom g, BcD bc, double *u, double *v, double *p, int san
             if (g.top) col[(size_t)(g.ny + 1) * P] = sanitize_val(col[(size_t)(g.ny + 1) * P], flag);
         }
         if (ii >= 1 && ii <= g.nx) { // apply_bc_p columns, bc.cpp:361-379
-            double first = col[P], last = col[(size_t)g.ny * P];
+            const bool whole = g.bottom && g.top;
+            double first = (both && !whole && g.top) ? farc[4 * P] : col[P];                    // p of the domain's first row
+            double last = (both && !whole && g.bottom) ? farc[4 * P] : col[(size_t)g.ny * P];   // ... and of its last row
             if (g.bottom) col[0] = both ? last : first;
             if (g.top) col[(size_t)(g.ny + 1) * P] = both ? first : last;
         }

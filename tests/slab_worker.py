@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--variant", type=int, default=1)
     ap.add_argument("--strip", type=int, default=0)  # > 0: force the streaming smoother with this strip height
     ap.add_argument("--p2p", type=int, default=1)  # 0: force the NCCL path (CFD_B200_P2P=0)
+    ap.add_argument("--bt-periodic", type=int, default=0)  # 1: bottom and top sides Periodic instead of the preset's
     ap.add_argument("--mg-mode", type=int, default=0)  # 1: the true V-cycle extension
     ap.add_argument("--mg-levels", type=int, default=3)
     ap.add_argument("--sweeps", type=int, default=2)
@@ -54,6 +55,8 @@ def main():
     s.set_variant(a.variant)
     s.set_smoother_strip(a.strip)
     bc, Re, CFL = cfd.preset(a.preset, a.Ly)
+    if a.bt_periodic:
+        bc.bottom.type = bc.top.type = cfd.PERIODIC
     pp = cfd.make_params(a.solver, vcycles=a.vcycles, tol=a.tol, pcg_max_iters=a.iters, mg_levels=a.mg_levels,
                          rbgs_sweeps=a.sweeps, mg_mode=a.mg_mode)
     r0, n = s.row0, s.nrows

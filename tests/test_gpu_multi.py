@@ -35,6 +35,8 @@ def run_slabs(n, tmp_path, **kw):
 def run_single(kw):
     cfd = importlib.import_module("macos-cfd_b200")
     bc, Re, CFL = cfd.preset(kw["preset"], kw.get("Ly", 1.0))
+    if kw.get("bt_periodic"):
+        bc.bottom.type = bc.top.type = cfd.PERIODIC
     s = cfd.Solver(kw["nx"], kw["ny"], kw.get("Lx", 2.0), kw.get("Ly", 1.0))
     s.set_smoother_strip(kw.get("strip", 0))
     if kw["preset"] == "shear":
@@ -120,3 +122,21 @@ def test_true_vcycle_on_slabs_matches_single_gpu(tmp_path, preset, nx, ny, level
     for name, a in (("u", u), ("v", v), ("p", p), ("rhs", rhs)):
         assert same(got[name], a), name
     assert np.allclose(got["hist"][:, 1], hist[:, 1], rtol=1e-10)
+
+
+@pytest.mark.parametrize("preset,solver", [("shear", "mg"), ("jet", "mg"), ("shear", "pcg")])
+def test_bottom_top_periodic_across_slabs(tmp_path, preset, solver):
+    """Both bottom/top Periodic (bc.cpp:171-183, :318-330, :361-379): the pass swaps the boundary rows of the two ends of the
+    domain, which live on the first and the last slab -- they trade those rows in front of the kernel.  Bit-identical to one
+    GPU (mg) / within the PCG tolerance, with the peer-memory transport for everything else."""
+    n = min(ngpu(), 4)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    kw = dict(preset=preset, solver=solver, nx=260, ny=203, steps=5, iters=50)
+    got = run_slabs(n, tmp_path, variant=1, p2p=1, **{"bt-periodic": 1}, **kw)
+    hist, (u, v, p, rhs), div_l2, vmax = run_single(dict(kw, bt_periodic=1))
+    for name, a in (("u", u), ("v", v), ("p", p)):
+        if solver == "mg":
+            assert same(got[name], a), name
+        else:
+            assert np.linalg.norm(got[name] - a) <= 1e-10 * np.linalg.norm(a), name
