@@ -199,8 +199,10 @@ int cfd_b200_pressure_solve(cfd_b200_solver *s, const cfd_b200_params *pp, doubl
 int cfd_b200_subtract_grad_p(cfd_b200_solver *s, double dt);
 
 /* ---- measurement ---- */
-/* ---- Readers / mutators around the step, single-GPU handles -------------------------------
- * An interactive caller can colour a frame and apply obstacles without the State ever crossing PCIe. */
+/* ---- Readers / mutators around the step ------------------------------------------------------
+ * An interactive caller can colour a frame and apply obstacles without the State ever crossing PCIe.  On a row-slab handle
+ * the calls are collective: `out` / `rgb` receive this slab's cell rows (cfd_b200_slab_rows), the statistics and the colour
+ * scale are those of the whole grid, shapes are given in cells of the whole grid. */
 /* ScalarField, viz.hpp:8 -- same order */
 enum { CFD_B200_FIELD_U = 0, CFD_B200_FIELD_V, CFD_B200_FIELD_SPEED, CFD_B200_FIELD_PRESSURE, CFD_B200_FIELD_VORTICITY,
        CFD_B200_FIELD_STREAMLINES, CFD_B200_FIELD_TEMPERATURE };

@@ -651,6 +651,11 @@ int reduce_fin(cfd_b200_solver *s, int kind, double tol, int max_iters, double *
         TRY(allreduce(s, &s->d_sc->diag_sum, 1, ncclSum));
         TRY(allreduce(s, &s->d_sc->diag_max_bits, 1, ncclMax));
         break;
+    case RED_VIZ:
+        TRY(allreduce(s, &s->d_sc->viz[0], 1, ncclMin));
+        TRY(allreduce(s, &s->d_sc->viz[1], 1, ncclMax));
+        TRY(allreduce(s, &s->d_sc->viz[2], 2, ncclSum));
+        break;
     default:
         return fail(CFD_B200_EINVAL, "bad reduction kind %d", kind);
     }
@@ -1874,12 +1879,17 @@ int cfd_b200_subtract_grad_p(cfd_b200_solver *s, double dt) {
 namespace {
 // compute_scalar on the device; leaves the field in s->viz_out and {min, max, sum, sum^2} in h_sc->viz
 int viz_scalar_device(cfd_b200_solver *s, int field) {
-    if (s->nranks > 1) return fail(CFD_B200_EUNSUPPORTED, "the visualisation entry points are single-GPU");
     if (field < 0 || field > VIZ_TEMPERATURE) return fail(CFD_B200_EINVAL, "bad scalar field %d", field);
     const Geom &g = s->g;
+    if (s->nranks > 1) { // row slabs: the vorticity reads u one row below / above the slab, every field v one row above
+        TRY(settle_halos(s));
+        if (!s->halo_uv_valid) TRY(halo_exchange2(s, s->u, s->v, 2, HALO_BOTH));
+        s->halo_uv_valid = true;
+    }
     if (!s->viz_out) CU(cudaMalloc(&s->viz_out, (size_t)g.nx * g.ny * sizeof(double)));
     dim3 grid(cdiv(g.nx, 256), g.ny < 128 ? g.ny : 128);
     LAUNCH(s, k_viz_scalar, grid, 256, g, s->u, s->v, s->p, field, s->viz_out, s->d_sc, s->partials);
+    TRY(reduce_fin(s, RED_VIZ, 0.0, 0)); // row slabs: minimum, maximum and the two sums over all slabs
     CU(cudaMemcpyAsync(s->h_sc, s->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s->stream));
     return 0;
 }
@@ -1900,7 +1910,7 @@ int cfd_b200_compute_scalar(cfd_b200_solver *s, int field, double *out, cfd_b200
         st->vmin = z[0];
         st->vmax = z[0] + span;
         // Gui::update_field_statistics, gui.cpp:1452-1474 (every value is finite after compute_scalar's own guard)
-        const double count = static_cast<double>(n);
+        const double count = static_cast<double>((size_t)s->g.nx * s->g.ny_glob);
         st->mean = z[2] / count;
         const double variance = (z[3] / count) - (st->mean * st->mean);
         st->stddev = std::sqrt(0.0 < variance ? variance : 0.0);
@@ -1934,9 +1944,9 @@ int cfd_b200_render_rgb(cfd_b200_solver *s, int field, int colormap, float scale
 
 int cfd_b200_apply_shapes(cfd_b200_solver *s, const cfd_b200_shape *shapes, int n) {
     if (!s || (n > 0 && !shapes) || n < 0) return fail(CFD_B200_EINVAL, "bad argument");
-    if (s->nranks > 1) return fail(CFD_B200_EUNSUPPORTED, "the shape masks are single-GPU");
     CU(cudaSetDevice(s->device));
     const Geom &g = s->g;
+    if (s->nranks > 1) TRY(settle_halos(s)); // row slabs: shapes are given in cells of the WHOLE grid; every slab masks its rows
     auto clampi = [](int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); };
     for (int k = 0; k < n; ++k) {
         const cfd_b200_shape &sh = shapes[k];
@@ -1944,14 +1954,17 @@ int cfd_b200_apply_shapes(cfd_b200_solver *s, const cfd_b200_shape *shapes, int 
         // bounding box in cells, float -> int truncation, clamped to the grid (shapes.cpp:12-30); a circle's box ends at
         // pos + size.x in both directions while its centre uses size.x/2 and size.y/2 (shapes.cpp:20-23, :42-44)
         const float ex = sh.pos_x + sh.size_x, ey = sh.type == 0 ? sh.pos_y + sh.size_y : sh.pos_y + sh.size_x;
-        const int i0 = clampi(static_cast<int>(sh.pos_x), 0, g.nx - 1), j0 = clampi(static_cast<int>(sh.pos_y), 0, g.ny - 1);
-        const int i1 = clampi(static_cast<int>(ex), 0, g.nx - 1), j1 = clampi(static_cast<int>(ey), 0, g.ny - 1);
+        const int i0 = clampi(static_cast<int>(sh.pos_x), 0, g.nx - 1), i1 = clampi(static_cast<int>(ex), 0, g.nx - 1);
+        int j0 = clampi(static_cast<int>(sh.pos_y), 0, g.ny_glob - 1), j1 = clampi(static_cast<int>(ey), 0, g.ny_glob - 1);
         if (i1 < i0 || j1 < j0) continue;
+        j0 = j0 < g.j0 ? g.j0 : j0, j1 = j1 > g.j0 + g.ny - 1 ? g.j0 + g.ny - 1 : j1; // the rows of the box inside this slab
+        if (j1 < j0) continue;
         const float cx = sh.pos_x + sh.size_x / 2.0f, cy = sh.pos_y + sh.size_y / 2.0f, rad = sh.size_x / 2.0f;
         LAUNCH(s, k_shape_apply, dim3(cdiv(i1 - i0 + 1, 256), j1 - j0 + 1), 256, g, s->u, s->v, i0, j0, i1, j1,
                sh.type != 0 ? 1 : 0, cx, cy, rad, sh.bc_type != 0 ? 1 : 0);
     }
     s->cfl_cached = false; // u, v changed behind the cached maxima
+    s->halo_uv_valid = false; // ... and behind the neighbours' copies of the slab's edge rows
     CU(cudaGetLastError());
     return 0;
 }

@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(256)
 // shapes.cpp:33-71 for ONE shape: every cell of the (host-clamped) box that lies inside the shape gets its left u face
 // and its bottom v face zeroed (solid) or scaled by 0.1 (porous).  One thread per cell; a cell owns those two faces,
 // so there are no write conflicts inside a shape; shapes are applied in order, one launch each.
+// (row slabs: j0 .. j1 are the rows of the box that fall into this slab, in GLOBAL cell rows; g.j0 maps them to local rows)
 __global__ void __launch_bounds__(256)
     k_shape_apply(Geom g, double *u, double *v, int i0, int j0, int i1, int j1, int circle, float cx, float cy, float rad,
                   int porous) { pdl_begin();
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(256)
         const float dx = (static_cast<float>(i) + 0.5f) - cx, dy = (static_cast<float>(j) + 0.5f) - cy;
         if (!(dx * dx + dy * dy <= rad * rad)) return;
     }
-    const size_t o = gidx(g, i + 1, j + 1);
+    const size_t o = gidx(g, i + 1, j - g.j0 + 1);
     if (porous) {
         u[o] *= 0.1;
         v[o] *= 0.1;

@@ -143,7 +143,8 @@ enum {
     RED_STEP_END,     // max|u|, max|v|, sum div^2 before / after (end of a step); + the deferred residual sum of the last smooth()
     RED_CFL,          // max|u|, max|v| (compute_cfl after an upload)
     RED_DIAG,         // divergence_l2 sum + max_velocity max
-    RED_VC            // 1 sum   -> mg_norm_tail (true V-cycle on row slabs: residual norm after a cycle)
+    RED_VC,           // 1 sum   -> mg_norm_tail (true V-cycle on row slabs: residual norm after a cycle)
+    RED_VIZ           // min, max, sum, sum of squares of the visualisation scalar (Scalars::viz)
 };
 struct RedArgs {
     P2PBlock *blk[P2P_MAXR]; // every rank's block (blk[rank] = mine)
@@ -180,6 +181,9 @@ __global__ void __launch_bounds__(P2P_RED_THREADS) k_p2p_reduce(RedArgs a, Scala
     case RED_DIAG:
         v0 = sc->diag_sum, v1 = __longlong_as_double((long long)sc->diag_max_bits);
         break;
+    case RED_VIZ:
+        v0 = sc->viz[0], v1 = sc->viz[1], v2 = sc->viz[2], v3 = sc->viz[3];
+        break;
     default:
         v0 = sc->red[0], v1 = sc->red[1];
     }
@@ -193,12 +197,14 @@ __global__ void __launch_bounds__(P2P_RED_THREADS) k_p2p_reduce(RedArgs a, Scala
     __syncthreads();
     if (t == 0) {
     const bool is_max0 = a.kind == RED_STEP_END || a.kind == RED_CFL, is_max1 = is_max0 || a.kind == RED_DIAG;
+    const bool viz = a.kind == RED_VIZ; // slot 0: minimum, slot 1: maximum (both start from the first rank's values)
     double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0, r4 = 0.0;
+    if (viz) r0 = me->red_val[par][0][0], r1 = me->red_val[par][0][1];
     for (int r = 0; r < a.nranks; ++r) { // fixed rank order: bit-identical on every rank
         const volatile double *slot = me->red_val[par][r];
         const double x0 = slot[0], x1 = slot[1];
-        r0 = is_max0 ? max2(r0, x0) : r0 + x0;
-        r1 = is_max1 ? max2(r1, x1) : r1 + x1;
+        r0 = viz ? min2(r0, x0) : is_max0 ? max2(r0, x0) : r0 + x0;
+        r1 = (viz || is_max1) ? max2(r1, x1) : r1 + x1;
         r2 += slot[2];
         r3 += slot[3];
         r4 += slot[4];
@@ -221,6 +227,9 @@ __global__ void __launch_bounds__(P2P_RED_THREADS) k_p2p_reduce(RedArgs a, Scala
         break;
     case RED_DIAG:
         sc->diag_sum = r0, sc->diag_max_bits = (unsigned long long)__double_as_longlong(r1);
+        break;
+    case RED_VIZ:
+        sc->viz[0] = r0, sc->viz[1] = r1, sc->viz[2] = r2, sc->viz[3] = r3;
         break;
     }
     } // t == 0

@@ -19,6 +19,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def viz_shapes(cfd, nx, ny):
+    """A solid box in the lower part, a porous circle that straddles the middle of the grid (slab boundaries), one disabled."""
+    return [cfd.Shape(0, nx * 0.2, ny * 0.1, nx * 0.1, ny * 0.15, 0, 1), cfd.Shape(1, nx * 0.5, ny * 0.42, ny * 0.2, ny * 0.2, 1, 1),
+            cfd.Shape(0, 1.0, 1.0, 5.0, 5.0, 0, 0)]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--preset", default="jet")
@@ -34,6 +40,7 @@ def main():
     ap.add_argument("--variant", type=int, default=1)
     ap.add_argument("--strip", type=int, default=0)  # > 0: force the streaming smoother with this strip height
     ap.add_argument("--p2p", type=int, default=1)  # 0: force the NCCL path (CFD_B200_P2P=0)
+    ap.add_argument("--viz", type=int, default=0)  # 1: obstacle masks + visualisation scalars / coloured frame after the steps
     ap.add_argument("--bt-periodic", type=int, default=0)  # 1: bottom and top sides Periodic instead of the preset's
     ap.add_argument("--mg-mode", type=int, default=0)  # 1: the true V-cycle extension
     ap.add_argument("--mg-levels", type=int, default=3)
@@ -70,16 +77,28 @@ def main():
             s.debug_delay(a.delay_us)  # the neighbours run ahead as far as the flag protocol lets them
         info = s.step(bc, Re, CFL, pp)
         hist.append((info.dt, info.residual, info.iters, info.div_before, info.div_after))
+    extra = {}
+    if a.viz:  # the GUI's per-frame mutators / readers on slabs: shapes in cells of the whole grid, whole-grid statistics
+        s.apply_shapes(viz_shapes(cfd, a.nx, a.ny))
+        for name in ("speed", "vorticity", "pressure"):
+            out, lo, hi, mean, std = s.compute_scalar(cfd.FIELDS[name])
+            extra[name], extra[name + "_stats"] = out, np.array([lo, hi, mean, std])
+        extra["rgb"] = s.render_rgb(cfd.FIELDS["speed"], 4)
+        info = s.step(bc, Re, CFL, pp)  # and a step on the masked State
     div_l2, vmax = s.divergence_l2(), s.max_velocity()
     u, v, p, rhs = s.download()
     # owned rows: u, p, rhs local rows 1..n; v rows 1..n (+ n+1 on the top slab); ghost rows from the end slabs
     top, bottom = rank == world - 1, rank == 0
     part = {"u": u[(0 if bottom else 1):(n + 2 if top else n + 1)], "v": v[(0 if bottom else 1):(n + 3 if top else n + 1)],
             "p": p[(0 if bottom else 1):(n + 2 if top else n + 1)], "rhs": rhs[(0 if bottom else 1):(n + 2 if top else n + 1)]}
+    for k in ("speed", "vorticity", "pressure", "rgb"):
+        if k in extra:
+            part[k] = extra[k]
     parts = [None] * world
     dist.gather_object(part, parts if rank == 0 else None, dst=0)
     if rank == 0:
-        out = {k: np.concatenate([q[k] for q in parts], axis=0) for k in ("u", "v", "p", "rhs")}
+        out = {k: np.concatenate([q[k] for q in parts], axis=0) for k in part}
+        out.update({k: v for k, v in extra.items() if k.endswith("_stats")})
         np.savez(a.out, hist=np.array(hist), div_l2=div_l2, vmax=vmax, comm_mode=s.comm_mode, **out)
     s.close()
     dist.destroy_process_group()

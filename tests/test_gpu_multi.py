@@ -140,3 +140,34 @@ def test_bottom_top_periodic_across_slabs(tmp_path, preset, solver):
             assert same(got[name], a), name
         else:
             assert np.linalg.norm(got[name] - a) <= 1e-10 * np.linalg.norm(a), name
+
+
+def test_shapes_and_visualisation_on_slabs(tmp_path):
+    """apply_shape_boundary_conditions / compute_scalar / the coloured frame on row slabs (collective calls; shapes in cells
+    of the whole grid, statistics and colour scale of the whole grid): fields and bytes identical to one GPU, and a step on
+    the masked State still is."""
+    n = min(ngpu(), 4)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import slab_worker
+    cfd = importlib.import_module("macos-cfd_b200")
+    kw = dict(preset="lid", solver="mg", nx=260, ny=203, steps=4)
+    got = run_slabs(n, tmp_path, variant=1, p2p=1, viz=1, **kw)
+    bc, Re, CFL = cfd.preset("lid", 1.0)
+    pp = cfd.make_params("mg", vcycles=2, tol=1e-8)
+    s = cfd.Solver(kw["nx"], kw["ny"], 2.0, 1.0)
+    for _ in range(kw["steps"]):
+        s.step(bc, Re, CFL, pp)
+    s.apply_shapes(slab_worker.viz_shapes(cfd, kw["nx"], kw["ny"]))
+    for name in ("speed", "vorticity", "pressure"):
+        out, lo, hi, mean, std = s.compute_scalar(cfd.FIELDS[name])
+        assert same(got[name], out), name
+        st = got[name + "_stats"]
+        assert st[0] == lo and st[1] == hi, name
+        assert abs(st[2] - mean) <= 1e-12 * abs(mean) + 1e-15 and abs(st[3] - std) <= 1e-10 * std, name
+    assert np.array_equal(got["rgb"], s.render_rgb(cfd.FIELDS["speed"], 4))
+    s.step(bc, Re, CFL, pp)
+    u, v, p, rhs = s.download()
+    for name, a in (("u", u), ("v", v), ("p", p)):
+        assert same(got[name], a), name
