@@ -252,9 +252,15 @@ void enqueue_cfl(cfd_b200_solver *s, double Re, double CFL, double dt_override, 
     LAUNCH(s, k_dt, 1, 1, g, Re, CFL, dt_override, s->d_sc, cfl_only);
 }
 
+// What the marching kernel covered (MODE 4 needs it for the fix-up of the divergence): marched = false when the grid is too
+// small for it and the tile kernel did everything.
+struct MarchRegion {
+    bool marched;
+    int XA, XB, YA, YB, RY;
+};
 template <int MODE>
-void enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, const double *vin, double *uout, double *vout,
-                 const double *uacc = nullptr, const double *vacc = nullptr, unsigned long long wait_epoch = 0) {
+MarchRegion enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, const double *vin, double *uout, double *vout,
+                        const double *uacc = nullptr, const double *vacc = nullptr, unsigned long long wait_epoch = 0) {
     if (!uacc) uacc = uout, vacc = vout; // MODE 2 in place
     const WaitArgs hw = wait_args(s, wait_epoch); // row slabs: the blocks that read the neighbours' rows wait for this send
     const Geom &g = s->g;
@@ -268,8 +274,9 @@ void enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, const doub
         rc.tx0[k] = tx0, rc.ty0[k] = ty0, rc.ntx[k] = ntx_;
         rc.end[k] = (k ? rc.end[k - 1] : 0) + ntx_ * nty_;
     };
+    constexpr int SMODE = MODE == 4 ? 2 : MODE; // the tile kernel has no divergence of its own
     auto launch_rects = [&]() {
-        if (rc.n > 0) LAUNCH(s, k_rhs_simple<MODE>, rc.end[rc.n - 1], block, g, k, uin, vin, uacc, vacc, uout, vout, s->d_sc, rc, hw);
+        if (rc.n > 0) LAUNCH(s, k_rhs_simple<SMODE>, rc.end[rc.n - 1], block, g, k, uin, vin, uacc, vacc, uout, vout, s->d_sc, rc, hw);
     };
     // Interior faces (all four fluxes MUSCL, for u and v alike): 2 <= ii <= nx-1, 2 <= jj <= ny-1.  The marching kernel
     // takes the part of it that is aligned to the simple kernel's tiles; the tile strips around it (ring included)
@@ -281,7 +288,7 @@ void enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, const doub
     if (s->variant == 0 || XB < XA + 16 || YB < YA + 8) {
         add(0, 0, ntx, nty);
         launch_rects();
-        return;
+        return MarchRegion{false, 0, 0, 0, 0, 0};
     }
     static const int ry_env = getenv("CFD_B200_RHS_RY") ? atoi(getenv("CFD_B200_RHS_RY")) : 0;
     // Rows per strip: 64 on grids that fill the GPU; smaller grids get shorter strips until the launch has one full
@@ -291,12 +298,14 @@ void enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, const doub
     while (RY > 8 && (long long)gxm * cdiv(YB - YA + 1, RY) < (long long)s->sm_count * MARCH_MINBLOCKS) RY /= 2;
     if (ry_env > 0) RY = ry_env;
     dim3 mgrid(gxm, cdiv(YB - YA + 1, RY));
-    LAUNCH(s, k_rhs_march<MODE>, mgrid, 32 * MARCH_WARPS, g, k, uin, vin, uacc, vacc, uout, vout, s->d_sc, XA, XB, YA, YB, RY, hw);
+    LAUNCH(s, k_rhs_march<MODE>, mgrid, 32 * MARCH_WARPS, g, k, uin, vin, uacc, vacc, uout, vout, s->d_sc, XA, XB, YA, YB, RY, hw,
+           MODE == 4 ? s->rhs : (double *)nullptr, s->partials);
     add(0, 0, ntx, tyb);                    // bottom strip
     add(0, tyt, ntx, nty - tyt);            // top strip
     add(0, tyb, 1, tyt - tyb);              // left strip
     add(txr, tyb, ntx - txr, tyt - tyb);    // right strip
     launch_rects();                         // one launch for all four
+    return MarchRegion{true, XA, XB, YA, YB, RY};
 }
 
 dim3 row_grid(const cfd_b200_solver *s, int ncols, int nrows, int *rows_per_block) {
@@ -1189,12 +1198,24 @@ int enqueue_step(cfd_b200_solver *s, const cfd_b200_bc *bc_in, double Re, double
     // them, out of place, together with the divergence of the result (k_project_div); otherwise everything is in place.
     const bool fused_div = s->variant == 1;
     double *us = fused_div ? s->ustar : s->u, *vs = fused_div ? s->vstar : s->v;
-    enqueue_rhs<2>(s, invRe, s->u1, s->v1, us, vs, s->u, s->v, ep); // :109-147
+    // :109-147; variant 1 also takes the divergence of u*, v* (:158-182) where the faces are final (k_rhs_march<4>)
+    static const int fuse_pre = getenv("CFD_B200_FUSE_PRE") ? atoi(getenv("CFD_B200_FUSE_PRE")) : 1;
+    MarchRegion mr{};
+    if (fused_div && fuse_pre) mr = enqueue_rhs<4>(s, invRe, s->u1, s->v1, us, vs, s->u, s->v, ep);
+    else mr = enqueue_rhs<2>(s, invRe, s->u1, s->v1, us, vs, s->u, s->v, ep), mr.marched = false;
     stage_mark(s, ST_BC2);
     enqueue_bc(s, bc, us, vs, nullptr, 1, 0); // :150-155
     TRY(halo_send2(s, vs, nullptr, 1, HALO_DOWN, &ep)); // the divergence of the top cell row reads the v face above it
     stage_mark(s, ST_DIV);
-    enqueue_divergence(s, 1, 1, 0, us, vs, ep); // :158-186; the blocks of the top cell row wait for that row
+    if (mr.marched) { // the cells the marching kernel could not close; the blocks of the top cell row wait for the neighbour's row
+        const long long nfix = (long long)g.ny * ((mr.XA - 1) + (g.nx - mr.XB + 1)) +
+                               (long long)((mr.YA - 1) + (mr.YB - mr.YA) / mr.RY + (g.ny - mr.YB + 1)) * g.nx;
+        const long long nblk = (nfix + 255) / 256, cap = 8LL * s->sm_count;
+        LAUNCH(s, k_div_fix_pre, (unsigned)(nblk < cap ? nblk : cap), 256, g, us, vs, s->rhs, s->p, s->d_sc, s->partials, mr.XA, mr.XB,
+               mr.YA, mr.YB, mr.RY, wait_args(s, ep));
+    } else {
+        enqueue_divergence(s, 1, 1, 0, us, vs, ep); // :158-186; the blocks of the top cell row wait for that row
+    }
     stage_mark(s, ST_SOLVE);
     int rc = enqueue_solve(s, pp, true); // :187
     if (rc) return rc;

@@ -71,10 +71,24 @@ __device__ __forceinline__ double shfl_up(double x) { return __shfl_up_sync(0xff
 
 // MODE as in k_rhs_simple (uacc / vacc: the accumulator read by MODE 2).  Outputs: ii in [XA, XB], jj in [YA, YB]; each block
 // row-strip covers RY rows.
+//
+// MODE 4 = MODE 2 + the divergence of what it produces (project.cpp:7-42 with the scaling of time_integrator.cpp:158-182):
+// a thread that has just formed u*, v* of row jj holds its own faces of rows jj-1 and jj and gets the u face right of its
+// pair from the lane above, so rhs = div(u*, v*) / dt of cell row jj-1 is written from registers and k_divergence<PRE> never
+// re-reads u*, v* (48 + 24 -> 56 bytes per cell).  Lane 31, which otherwise only feeds its neighbours, forms u* of its first
+// column for that purpose (one extra load per row: the u1 column right of the warp's 64).  Cells this kernel closes:
+// columns [XA, XB-1], rows [YA, YB-1] except the top row of every strip; k_div_fix_pre does the others -- the tile strips
+// around the marching region, whose faces come from k_rhs_simple and the boundary pass, and those strip-top rows.
+#ifndef MARCH_MINBLOCKS_DIV
+#define MARCH_MINBLOCKS_DIV 4
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(32 * MARCH_WARPS, MARCH_MINBLOCKS)
+__global__ void __launch_bounds__(32 * MARCH_WARPS, MODE == 4 ? MARCH_MINBLOCKS_DIV : MARCH_MINBLOCKS)
     k_rhs_march(Geom g, RhsConst k, const double *__restrict__ uin, const double *__restrict__ vin, const double *uacc,
-                const double *vacc, double *uout, double *vout, Scalars *sc, int XA, int XB, int YA, int YB, int RY, WaitArgs hw) { pdl_begin();
+                const double *vacc, double *uout, double *vout, Scalars *sc, int XA, int XB, int YA, int YB, int RY, WaitArgs hw,
+                double *rhs, double *partials) { pdl_begin();
+    constexpr bool HEUN = MODE == 2 || MODE == 4, DIV = MODE == 4;
+    double dacc[1] = {0.0};
     // the first strip of rows goes to the LAST blocks of the grid (see k_rbgs_stream: strips that wait for a neighbour's rows
     // should be scheduled when the rows are there)
     const int by = blockIdx.y + 1 == gridDim.y ? 0 : (int)blockIdx.y + 1;
@@ -85,7 +99,7 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS, MARCH_MINBLOCKS)
     const int lane = threadIdx.x & 31;
     const int wx = blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
     const int X0 = XA - 2 + MARCH_COLS * wx; // raw column of lane 0's first column (odd => aligned double2)
-    if (X0 + 2 > XB) return;                 // whole warp outside
+    if (X0 + 2 > XB) return;                 // whole warp outside (before any shuffle: the rest is convergent code)
     const int a = X0 + 2 * lane;             // this thread's columns: a, a+1
     const int y0 = YA + by * RY;
     const int y1 = min(y0 + RY - 1, YB);
@@ -100,6 +114,13 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS, MARCH_MINBLOCKS)
     const bool st_a = lane >= 1 && lane <= 30 && a >= XA && a <= XB;
     const bool st_b = lane >= 1 && lane <= 30 && a + 1 >= XA && a + 1 <= XB;
     int flag = 0;
+    // MODE 4: lane 31 forms u* of its first column (the face right of lane 30's pair); cells this thread closes
+    const bool ext = DIV && lane == 31 && a <= XB;
+    const bool cA = DIV && st_a && st_b, cB = DIV && st_b && a + 2 <= XB;
+    const double inv_dt = DIV ? sc->inv_dt : 0.0;
+    double2 pun = make_double2(0.0, 0.0), pvn = make_double2(0.0, 0.0); // u*, v* of the row below
+    double urn = 0.0;                                                     // u*(a+2) of the row below
+    double xq = ext ? pu[(size_t)y0 * P + 2] : 0.0;                       // u1(a+2, jj) for lane 31
 
     MarchCol U[2], V[2];
     // ---- prologue: rows y0-2 .. y0+1 -> state at jj = y0 (fym = flux through the face between y0-1 and y0)
@@ -132,9 +153,11 @@ _Pragma(MARCH_STR(unroll MARCH_UNROLL))
             pre_u = ld2(pu, jj + 3);
             pre_v = ld2(pv, jj + 3);
         }
+        const double xq_now = xq;
+        if (ext && jj < y1) xq = pu[(size_t)(jj + 1) * P + 2];
         const size_t o = gidx(g, a, jj);
         double2 au = make_double2(0.0, 0.0), av = make_double2(0.0, 0.0);
-        if (MODE == 2 && (st_a || st_b)) { // s.u / s.v (uacc may be uout: only this thread touches these elements)
+        if (HEUN && (st_a || st_b || ext)) { // s.u / s.v (uacc may be uout: only this thread touches these elements)
             au = *reinterpret_cast<const double2 *>(uacc + o);
             av = *reinterpret_cast<const double2 *>(vacc + o);
         }
@@ -152,7 +175,8 @@ _Pragma(MARCH_STR(unroll MARCH_UNROLL))
             double fyb = flux_shared(C[1].q0, C[1].hs0, C[1].q1, hs1b, vb);
             // ---- x direction on row jj, shared across the warp (advection.cpp:52-81, :280-309)
             const double qa = C[0].q0, qb = C[1].q0;
-            const double qa_n = shfl_dn(qa); // q(a+2)
+            double qa_n = shfl_dn(qa);       // q(a+2)
+            if (DIV && f == 0 && lane == 31) qa_n = xq_now;
             const double qb_p = shfl_up(qb); // q(a-1)
             double dxp = qa - qb_p, dxa = qb - qa, dxb = qa_n - qb;
             double hsa = half_minmod(dxp, dxa), hsb = half_minmod(dxa, dxb);
@@ -170,10 +194,11 @@ _Pragma(MARCH_STR(unroll MARCH_UNROLL))
             db = db + k.invRe * lapb;
             // slow path (overflow / non-finite input only): the reference formula, clip included, straight from memory
             const double *qg = (f ? vin : uin) + o;
-            if (st_a && !finite_d(da)) da = rhs_point_slow(qg, uin + o, vin + o, (int)P, k.idx, k.idy, k.idx2, k.idy2, k.invRe);
+            const bool need_a = st_a || (ext && f == 0);
+            if (need_a && !finite_d(da)) da = rhs_point_slow(qg, uin + o, vin + o, (int)P, k.idx, k.idy, k.idx2, k.idy2, k.invRe);
             if (st_b && !finite_d(db)) db = rhs_point_slow(qg + 1, uin + o + 1, vin + o + 1, (int)P, k.idx, k.idy, k.idx2, k.idy2, k.invRe);
             double *d = f ? dv : du;
-            d[0] = st_a ? sanitize_val(da, flag) : 0.0; // lanes that only feed their neighbours hold no result
+            d[0] = need_a ? sanitize_val(da, flag) : 0.0; // lanes that only feed their neighbours hold no result
             d[1] = st_b ? sanitize_val(db, flag) : 0.0;
             // ---- rotate the y-state
             C[0].qm1 = C[0].q0; C[0].q0 = C[0].q1; C[0].q1 = q2a; C[0].dy0 = dy1a; C[0].hs0 = hs1a; C[0].fym = fya;
@@ -203,6 +228,101 @@ _Pragma(MARCH_STR(unroll MARCH_UNROLL))
             uout[o + 1] = ou.y;
             vout[o + 1] = ov.y;
         }
+        if (DIV) { // divergence of cell row jj-1 (its per-value guards are identities: u*, v* were sanitised above)
+            const double uright = shfl_dn(ou.x); // u*(a+2, jj): an output of the lane above, or lane 31's extra column
+            if (jj > y0) {
+                const double dA = fin0((pun.y - pun.x) * k.idx + (ov.x - pvn.x) * k.idy);
+                const double dB = fin0((urn - pun.y) * k.idx + (ov.y - pvn.y) * k.idy);
+                double *pr = rhs + o - P;
+                if (cA && cB) {
+                    *reinterpret_cast<double2 *>(pr) = make_double2(fin0(dA * inv_dt), fin0(dB * inv_dt));
+                    dacc[0] += dA * dA;
+                    dacc[0] += dB * dB;
+                } else if (cA) {
+                    pr[0] = fin0(dA * inv_dt);
+                    dacc[0] += dA * dA;
+                } else if (cB) {
+                    pr[1] = fin0(dB * inv_dt);
+                    dacc[0] += dB * dB;
+                }
+            }
+            pun = ou, pvn = ov, urn = uright;
+        }
     }
     if (flag) sc->nonfinite_any = 1;
+    if (DIV) {
+        // Sum of squares over the grid, one partial per WARP (the warps of a block are independent of each other here and
+        // the ones outside the region have left): shuffle tree -> slot of this warp -> the last warp to arrive (ticket) adds
+        // the slots in a fixed order.  Deterministic like grid_sum; k_div_fix_pre adds its part and finishes div_before.
+        const int nwx = (XB - XA) / MARCH_COLS + 1, nlive = nwx * (int)gridDim.y;
+        double x = dacc[0];
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) x += __shfl_down_sync(0xffffffffu, x, o2);
+        int last = 0;
+        if (lane == 0) {
+            partials[wx + nwx * (int)blockIdx.y] = x;
+            __threadfence();
+            last = atomicAdd(&sc->ticket[0], 1u) == (unsigned)(nlive - 1);
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            __threadfence();
+            double t = 0.0;
+            for (int i = lane; i < nlive; i += 32) t += __ldcg(&partials[i]);
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) t += __shfl_down_sync(0xffffffffu, t, o2);
+            if (lane == 0) sc->ticket[0] = 0u, sc->div_before = t;
+        }
+    }
+}
+
+// The cells k_rhs_march<4> leaves open, behind the boundary pass on u*, v*: the rows below YA and from YB up, the top row of
+// every strip of RY rows, and in the other rows the columns left of XA and from XB on.  Exactly k_divergence<PRE> on those
+// cells; adds its sum of squares to the marching kernel's, finishes div_before (time_integrator.cpp:162-171) and sets
+// s.p(0,0) = 0 (:186).  The blocks of the full rows come last: on a slab below another one the top cell row reads the
+// neighbour's v* row and waits for it there.
+__device__ __forceinline__ bool dfp_full_row(int r, int YA, int YB, int RY) { return r < YA || r >= YB || (r - YA + 1) % RY == 0; }
+__global__ void __launch_bounds__(256)
+    k_div_fix_pre(Geom g, const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ rhs, double *p,
+                  Scalars *sc, double *partials, int XA, int XB, int YA, int YB, int RY, WaitArgs hw) { pdl_begin();
+    const int nside = (XA - 1) + (g.nx - XB + 1);                // columns 1 .. XA-1 and XB .. nx
+    const int ntop = (YB - YA) / RY;                             // strip tops below YB: YA + m RY - 1, m = 1 .. ntop
+    const int nfull = (YA - 1) + ntop + (g.ny - YB + 1);         // full rows
+    const long long n_side = (long long)g.ny * nside, ntot = n_side + (long long)nfull * g.nx;
+    const long long chunk = (long long)blockDim.x * gridDim.x;
+    // row ny is the last full row: the blocks that can reach its cells wait for the neighbour's v* row (row slabs)
+    {
+        const long long first = (long long)blockIdx.x * blockDim.x;
+        bool reach = false;
+        for (long long b = first; b < ntot; b += chunk)
+            if (b + blockDim.x > ntot - g.nx) reach = true;
+        p2p_wait_block(hw, false, reach, sc);
+    }
+    const double inv_dt = sc->inv_dt;
+    double acc[1] = {0.0};
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < ntot; k += chunk) {
+        int ii, jj;
+        if (k < n_side) {
+            jj = 1 + (int)(k / nside);
+            const int c = (int)(k - (long long)(jj - 1) * nside);
+            ii = c < XA - 1 ? 1 + c : XB + (c - (XA - 1));
+            if (dfp_full_row(jj, YA, YB, RY)) continue; // that cell goes with its row
+        } else {
+            const long long q = k - n_side;
+            const int rr = (int)(q / g.nx);
+            ii = 1 + (int)(q - (long long)rr * g.nx);
+            jj = rr < YA - 1 ? 1 + rr : (rr < YA - 1 + ntop ? YA + (rr - (YA - 1) + 1) * RY - 1 : YB + (rr - (YA - 1) - ntop));
+        }
+        const size_t o = gidx(g, ii, jj);
+        const double uR = fin0(u[o + 1]), uL = fin0(u[o]), vT = fin0(v[o + g.P]), vB = fin0(v[o]);
+        double d = fin0((uR - uL) * g.idx + (vT - vB) * g.idy);
+        acc[0] += d * d;
+        rhs[o] = fin0(d * inv_dt);
+    }
+    if (p && blockIdx.x == 0 && threadIdx.x == 0 && g.j0 == 0) p[gidx(g, 1, 1)] = 0.0; // s.p(0,0) = 0 before the solve
+    const double ncell = (double)(g.nx * g.ny_glob);
+    grid_sum<1>(acc, partials, &sc->ticket[0], [=](double(&t)[1]) {
+        const double total = sc->div_before + t[0];
+        sc->div_before = (g.ny == g.ny_glob) ? sqrt(total / ncell) : total; // slabs finish after the allreduce
+    });
 }
