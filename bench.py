@@ -645,7 +645,8 @@ def main():
                  "steps": k, "warmup": 3, "ms_per_step": r["ms_per_step"], "value": r["value"], "unit": "cell-updates/s",
                  "gpu_launches": r["gpu_launches"], "last_step": r["last_step"],
                  "roofline": {k2: rf[k2] for k2 in ("kernel", "achieved", "peak", "frac", "traffic", "ms_per_launch", "launches_per_step")},
-                 "whole_step_frac": rf["whole_step"]["frac"], "stages": rf["stages"]}
+                 "whole_step_frac": rf["whole_step"]["frac"], "stages": rf["stages"],
+                 "peer_wait_us_per_step_rank0": r["config"].get("peer_wait_us_per_step_rank0")}
             if "parity" in r:
                 e["parity"] = r["parity"]
             also.append(e)
