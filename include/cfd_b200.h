@@ -237,6 +237,10 @@ int cfd_b200_stage_times(cfd_b200_solver *s, int n, const char **names, float *m
 void *cfd_b200_stream(cfd_b200_solver *s);
 /* Tuning switch for A/B measurements: 0 = simple kernels, 1 = optimised kernels (default). */
 int cfd_b200_set_variant(cfd_b200_solver *s, int variant);
+/* Which marching advection + diffusion + Runge-Kutta kernel the optimised path launches: 2 = k_rhs_march2 (default; slow path
+ * deferred behind the loop), 1 = the first version (slow path inside the loop).  Same results bit for bit; for A/B timing.
+ * The environment variable CFD_B200_MARCH sets the default of new handles. */
+int cfd_b200_set_march_kernel(cfd_b200_solver *s, int version);
 
 #ifdef __cplusplus
 }

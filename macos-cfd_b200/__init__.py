@@ -177,6 +177,7 @@ def load_library(build: bool = True):
     L.cfd_b200_stream.argtypes = [S]
     L.cfd_b200_stream.restype = C.c_void_p
     L.cfd_b200_set_variant.argtypes = [S, C.c_int]
+    L.cfd_b200_set_march_kernel.argtypes = [S, C.c_int]
     _lib = L
     return L
 
@@ -391,6 +392,10 @@ class Solver:
 
     def set_variant(self, v):
         self._check(self.L.cfd_b200_set_variant(self.h, int(v)))
+
+    def set_march_kernel(self, version):
+        """2 = k_rhs_march2 (default), 1 = the first marching kernel (A/B timing; identical results)."""
+        self._check(self.L.cfd_b200_set_march_kernel(self.h, int(version)))
 
     def stage_times(self):
         names = (C.c_char_p * 16)()

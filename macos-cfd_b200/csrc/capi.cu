@@ -17,6 +17,7 @@
 #include "kernels_pressure.cuh"
 #include "kernels_step.cuh"
 #include "kernels_rhs_march.cuh"
+#include "kernels_rhs_march2.cuh"
 #include "kernels_rbgs_fused.cuh"
 #include "kernels_rbgs_stream.cuh"
 #include "kernels_vcycle.cuh"
@@ -81,7 +82,7 @@ struct cfd_b200_solver {
         cfd_b200_bc bc{};
         cfd_b200_params pp{};
         double Re = 0, CFL = 0, dt_override = 0;
-        int variant = 0, rb_strip = 0;
+        int variant = 0, rb_strip = 0, march_kernel = 0;
         double *p = nullptr;
         long long launches = 0;
         bool swaps_p = false;
@@ -94,6 +95,7 @@ struct cfd_b200_solver {
     double defer_tol = 0.0;
     long long launches = 0;
     int variant = 1;
+    int march_kernel = -1; // marching advection kernel: 2 = k_rhs_march2 (default), 1 = first version; -1 = CFD_B200_MARCH not read yet
     int rb_strip = 0;      // > 0: force the streaming smoother with this many rows per strip (tests, tuning)
     int last_smoother = 0; // which kernel ran the last smooth(): 1 streaming, 2 tile, 3 per-colour passes
     int last_pcg = 0;      // which kernels ran the last PCG solve: 1 cooperative persistent, 2 streaming, 3 tiles
@@ -298,8 +300,19 @@ MarchRegion enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, con
     while (RY > 8 && (long long)gxm * cdiv(YB - YA + 1, RY) < (long long)s->sm_count * MARCH_MINBLOCKS) RY /= 2;
     if (ry_env > 0) RY = ry_env;
     dim3 mgrid(gxm, cdiv(YB - YA + 1, RY));
-    LAUNCH(s, k_rhs_march<MODE>, mgrid, 32 * MARCH_WARPS, g, k, uin, vin, uacc, vacc, uout, vout, s->d_sc, XA, XB, YA, YB, RY, hw,
-           MODE == 4 ? s->rhs : (double *)nullptr, s->partials);
+    // k_rhs_march2 (kernels_rhs_march2.cuh) defers its slow path: inputs, accumulators and outputs must not alias (in-place
+    // stage 2 of `variant = 2` does), a thread stores both of its columns or none (XA odd, XB even) and indexes a field with
+    // 32 bits.  Anything else, and CFD_B200_MARCH=1 / cfd_b200_set_march_kernel(s, 1), runs the first version.
+    if (s->march_kernel < 0) s->march_kernel = getenv("CFD_B200_MARCH") ? atoi(getenv("CFD_B200_MARCH")) : 2;
+    const bool heun = MODE == 2 || MODE == 4; // the others never read uacc / vacc (set to the outputs above)
+    const bool v2 = s->march_kernel != 1 && (!heun || (uacc != uout && vacc != vout)) && uin != uout && vin != vout && (XA & 1) && !(XB & 1) &&
+                    (unsigned long long)g.rows * (unsigned long long)g.P < (1ULL << 32);
+    if (v2)
+        LAUNCH(s, k_rhs_march2<MODE>, mgrid, 32 * MARCH_WARPS, g, k, uin, vin, uacc, vacc, uout, vout, s->d_sc, XA, XB, YA, YB, RY,
+               hw, MODE == 4 ? s->rhs : (double *)nullptr, s->partials);
+    else
+        LAUNCH(s, k_rhs_march<MODE>, mgrid, 32 * MARCH_WARPS, g, k, uin, vin, uacc, vacc, uout, vout, s->d_sc, XA, XB, YA, YB, RY, hw,
+               MODE == 4 ? s->rhs : (double *)nullptr, s->partials);
     add(0, 0, ntx, tyb);                    // bottom strip
     add(0, tyt, ntx, nty - tyt);            // top strip
     add(0, tyb, 1, tyt - tyb);              // left strip
@@ -1437,6 +1450,15 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
                 break;
             }
         }
+        {   // k_rhs_march2: 4 blocks per SM of 16 / 33 KB of (static) shared memory each
+            auto prep = [](auto kernel) {
+                return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
+            };
+            if (!prep(k_rhs_march2<0>) || !prep(k_rhs_march2<1>) || !prep(k_rhs_march2<2>) || !prep(k_rhs_march2<4>)) {
+                rc = fail(CFD_B200_ECUDA, "cudaFuncSetAttribute(k_rhs_march2) failed: %s", cudaGetErrorString(cudaGetLastError()));
+                break;
+            }
+        }
         if (cudaMalloc(&s->partials, s->partials_n * sizeof(double)) != cudaSuccess) { rc = fail(CFD_B200_ENOMEM, "partials alloc failed"); break; }
         for (int i = 0; i < ST_COUNT; ++i)
             if (cudaEventCreate(&s->ev[i]) != cudaSuccess) { rc = fail(CFD_B200_ECUDA, "event create failed"); break; }
@@ -1588,7 +1610,7 @@ int cfd_b200_step_async(cfd_b200_solver *s, const cfd_b200_bc *bc, double Re, do
     }
     auto matches = [&](const cfd_b200_solver::StepGraph &g) {
         return g.exec && g.p == s->p && bc_equal(g.bc, *bc) && g.Re == Re && g.CFL == CFL && g.dt_override == dt_override &&
-               g.variant == s->variant && g.rb_strip == s->rb_strip && g.pp.vcycles == pp->vcycles && g.pp.tol == pp->tol &&
+               g.variant == s->variant && g.march_kernel == s->march_kernel && g.rb_strip == s->rb_strip && g.pp.vcycles == pp->vcycles && g.pp.tol == pp->tol &&
                g.pp.mg_levels == pp->mg_levels && g.pp.rbgs_sweeps == pp->rbgs_sweeps;
     };
     for (auto &g : s->step_graph)
@@ -1619,7 +1641,7 @@ int cfd_b200_step_async(cfd_b200_solver *s, const cfd_b200_bc *bc, double Re, do
     if (rc == 0 && ec == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
         cudaGraphDestroy(graph);
         slot->exec = exec, slot->bc = *bc, slot->pp = *pp, slot->Re = Re, slot->CFL = CFL, slot->dt_override = dt_override;
-        slot->variant = s->variant, slot->rb_strip = s->rb_strip, slot->p = p0, slot->launches = s->launches - l0;
+        slot->variant = s->variant, slot->march_kernel = s->march_kernel, slot->rb_strip = s->rb_strip, slot->p = p0, slot->launches = s->launches - l0;
         slot->swaps_p = s->p != p0, slot->last_smoother = s->last_smoother;
         CU(cudaGraphLaunch(exec, s->stream)); // the capture recorded the step, it did not run it
         return 0;
@@ -2017,6 +2039,13 @@ void *cfd_b200_stream(cfd_b200_solver *s) { return s ? (void *)s->stream : nullp
 int cfd_b200_set_variant(cfd_b200_solver *s, int variant) {
     if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
     s->variant = variant;
+    return 0;
+}
+
+int cfd_b200_set_march_kernel(cfd_b200_solver *s, int version) {
+    if (!s) return fail(CFD_B200_EINVAL, "solver is NULL");
+    if (version != 1 && version != 2) return fail(CFD_B200_EINVAL, "march kernel version must be 1 or 2");
+    s->march_kernel = version;
     return 0;
 }
 
