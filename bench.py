@@ -56,12 +56,13 @@ DEFAULT_WORKLOAD = "jet_mg_8192"
 #   mg  : the smoother moves 24 B/cell per smooth() launch (R p, R rhs, W p; SURVEY's per-pass accounting: 64)
 #   PCG : phase 1 + phase 2 move 24 + 40 = 64 B/cell per iteration (Ap recomputed, z never stored; SURVEY: 80), + 24 init
 # The CFL maxima (16 B/cell in SURVEY) ride on the post-projection divergence kernel and cost no pass of their own.
-# RK stage 2 also writes rhs = div(u*, v*) / dt of the cells it can close (k_rhs_march<4>: 48 + 24 -> 56 B/cell) and the
+# RK stage 2 also writes rhs = div(u*, v*) / dt of the cells it can close (k_rhs_march2<4>: 48 + 24 -> 56 B/cell) and the
 # projection the post-projection divergence (k_project_div: 40 + 24 -> 48 B/cell); "divergence" / "divergence_post" are what is
 # left of the two: the fix-up kernels on a few per cent of the cells.
 STAGE_BYTES = {"cfl_dt": 0, "rhs_stage1": 32, "rhs_stage2": 56, "divergence": 0, "project": 48, "divergence_post": 0}
 SURVEY_STEP_BYTES = {"mg": lambda vcycles, iters: 184 + 64 * vcycles, "pcg": lambda vcycles, iters: 184 + 32 + 80 * iters}
-STAGE_KERNEL = {"rhs_stage1": "k_rhs_march<1>", "rhs_stage2": "k_rhs_march<4>", "divergence": "k_div_fix_pre",
+_MARCH = "k_rhs_march" if os.environ.get("CFD_B200_MARCH") == "1" else "k_rhs_march2"  # capi.cu: enqueue_rhs picks the same way
+STAGE_KERNEL = {"rhs_stage1": _MARCH + "<1>", "rhs_stage2": _MARCH + "<4>", "divergence": "k_div_fix_pre",
                 "project": "k_project_div", "divergence_post": "k_div_fix"}
 PCG_KERNEL = "k_pcg_phase1_march + k_pcg_phase2_march (one iteration)"
 

@@ -74,6 +74,11 @@ struct cfd_b200_solver {
     cudaStream_t stream = nullptr;
     cudaStream_t comm_stream = nullptr; // row slabs: the one-way sends run here, next to the solver's kernels
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // The tile kernel of the ring strips (5 % of the faces, 35 us of small blocks at 8192^2) runs here, next to the marching
+    // kernel of the same stage instead of behind it; CFD_B200_AUX=0 keeps both in the solver's stream.
+    cudaStream_t aux_stream = nullptr;
+    cudaStream_t launch_stream = nullptr; // non-null: where launch_kp puts the next kernels (set and cleared around a forked launch)
+    cudaEvent_t ev_afork = nullptr, ev_ajoin = nullptr;
     // Captured CUDA graph of a steady-state step (single GPU, reference-mode mg): replayed while the step's arguments, the
     // launch sequence (cached CFL maxima, same BC) and the roles of p / p_alt stay what they were at capture time.  Two slots:
     // an odd number of smooth() calls per step swaps p and p_alt, so consecutive steps alternate between two graphs.
@@ -138,7 +143,7 @@ namespace {
 template <class... KArgs, class... Args>
 inline void launch_kp(cfd_b200_solver *s, int pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s->stream;
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s->launch_stream ? s->launch_stream : s->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -295,11 +300,38 @@ MarchRegion enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, con
     static const int ry_env = getenv("CFD_B200_RHS_RY") ? atoi(getenv("CFD_B200_RHS_RY")) : 0;
     // Rows per strip: 64 on grids that fill the GPU; smaller grids get shorter strips until the launch has one full
     // wave of blocks (148 SMs x MARCH_MINBLOCKS) -- at 1024^2, 64-row strips are only 80 blocks (2 warps per SM).
-    int RY = 64;
+    // 128 where that still gives two full waves (8192^2: 2.398 -> 2.377 ms per step: 4 of 132 rows read twice instead of 4 of 68).
     const int gxm = cdiv(cdiv(XB - XA + 1, MARCH_COLS), MARCH_WARPS);
+    int RY = (long long)gxm * cdiv(YB - YA + 1, 128) >= 2LL * s->sm_count * MARCH_MINBLOCKS ? 128 : 64;
     while (RY > 8 && (long long)gxm * cdiv(YB - YA + 1, RY) < (long long)s->sm_count * MARCH_MINBLOCKS) RY /= 2;
     if (ry_env > 0) RY = ry_env;
     dim3 mgrid(gxm, cdiv(YB - YA + 1, RY));
+    add(0, 0, ntx, tyb);                    // bottom strip
+    add(0, tyt, ntx, nty - tyt);            // top strip
+    add(0, tyb, 1, tyt - tyb);              // left strip
+    add(txr, tyb, ntx - txr, tyt - tyb);    // right strip
+    // One launch for all four strips.  It writes other faces than the marching kernel and reads the same inputs, so it runs
+    // beside it on the auxiliary stream (forked here, joined behind the marching kernel's launch; in-place stage 2 of
+    // `variant = 2` keeps the old order: there the tile kernel reads faces next to the ones the marching kernel overwrites).
+    const bool fork = s->aux_stream && rc.n > 0 && uin != uout && vin != vout && (!(MODE == 2 || MODE == 4) || (uacc != uout && vacc != vout));
+    if (fork) {
+        cudaEventRecord(s->ev_afork, s->stream);
+        cudaStreamWaitEvent(s->aux_stream, s->ev_afork, 0);
+        s->launch_stream = s->aux_stream;
+        const int pdl = s->pdl;
+        s->pdl = 0; // its predecessor in that stream is an event, not a kernel
+        launch_rects();
+        s->pdl = pdl;
+        s->launch_stream = nullptr;
+    }
+    auto join_strips = [&]() {
+        if (fork) {
+            cudaEventRecord(s->ev_ajoin, s->aux_stream);
+            cudaStreamWaitEvent(s->stream, s->ev_ajoin, 0);
+        } else {
+            launch_rects();
+        }
+    };
     // k_rhs_march2 (kernels_rhs_march2.cuh) defers its slow path: inputs, accumulators and outputs must not alias (in-place
     // stage 2 of `variant = 2` does), a thread stores both of its columns or none (XA odd, XB even) and indexes a field with
     // 32 bits.  Anything else, and CFD_B200_MARCH=1 / cfd_b200_set_march_kernel(s, 1), runs the first version.
@@ -313,11 +345,7 @@ MarchRegion enqueue_rhs(cfd_b200_solver *s, double invRe, const double *uin, con
     else
         LAUNCH(s, k_rhs_march<MODE>, mgrid, 32 * MARCH_WARPS, g, k, uin, vin, uacc, vacc, uout, vout, s->d_sc, XA, XB, YA, YB, RY, hw,
                MODE == 4 ? s->rhs : (double *)nullptr, s->partials);
-    add(0, 0, ntx, tyb);                    // bottom strip
-    add(0, tyt, ntx, nty - tyt);            // top strip
-    add(0, tyb, 1, tyt - tyb);              // left strip
-    add(txr, tyb, ntx - txr, tyt - tyb);    // right strip
-    launch_rects();                         // one launch for all four
+    join_strips();
     return MarchRegion{true, XA, XB, YA, YB, RY};
 }
 
@@ -1408,6 +1436,13 @@ int cfd_b200_create_slab(int nx, int ny, double Lx, double Ly, int device, int r
         if (nranks > 1 && (cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
                            cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
                            cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess)) { rc = fail(CFD_B200_ECUDA, "communication stream create failed"); break; }
+        if (!(getenv("CFD_B200_AUX") && atoi(getenv("CFD_B200_AUX")) == 0)) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi); // hi = greatest priority: the strips' small blocks go first
+            if (cudaStreamCreateWithPriority(&s->aux_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+                cudaEventCreateWithFlags(&s->ev_afork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&s->ev_ajoin, cudaEventDisableTiming) != cudaSuccess) { rc = fail(CFD_B200_ECUDA, "auxiliary stream create failed"); break; }
+        }
         {   // one arena (a multiple of 2 MiB: its own mapping, one IPC handle): NFIELDS fields + this rank's P2PBlock
             size_t bytes = NFIELDS * s->n * sizeof(double) + sizeof(P2PBlock);
             bytes = (bytes + (2u << 20) - 1) / (2u << 20) * (2u << 20);
@@ -1520,6 +1555,9 @@ void cfd_b200_destroy(cfd_b200_solver *s) {
     for (auto &g : s->step_graph)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+    if (s->aux_stream) cudaStreamDestroy(s->aux_stream);
+    if (s->ev_afork) cudaEventDestroy(s->ev_afork);
+    if (s->ev_ajoin) cudaEventDestroy(s->ev_ajoin);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->stream) cudaStreamDestroy(s->stream);

@@ -21,7 +21,7 @@ def short(name):
     """'void k_rhs_march<1>(Geom, ...)' -> 'k_rhs_march<1>'; 'k_rbgs_stream<1, 0>' -> 'k_rbgs_stream'."""
     m = re.search(r"(k_[a-z0-9_]+)(<[^>]*>)?", name)
     base, targs = m.group(1), m.group(2) or ""
-    if base in ("k_rhs_march", "k_divergence", "k_rhs_fused2"):
+    if base in ("k_rhs_march", "k_rhs_march2", "k_divergence", "k_rhs_fused2"):
         return base + targs.replace(" ", "")
     return base
 
