@@ -374,6 +374,63 @@ def test_nonfinite_input_is_sanitised_like_the_reference(cfd, port):
     assert same(gu, sim.u) and same(gv, sim.v) and same(gp, sim.p) and same(grhs[1:-1, 1:-1], sim.rhs[1:-1, 1:-1])
 
 
+@pytest.mark.parametrize("march", [2, 1])
+@pytest.mark.parametrize("preset,nx,ny,dt_override", [("lid", 300, 211, 0.0), ("jet", 257, 130, 2.5e-4), ("shear", 130, 67, 1e-3),
+                                                       ("lid", 560, 300, 1e-3)])
+def test_slow_path_of_the_marching_kernel_inside_a_step(cfd, port, preset, nx, ny, dt_override, march):
+    """Overflowing differences, infinities and NaNs INSIDE the marching kernels' region, through whole steps: the values
+    k_rhs_march2 repairs behind its loop (RK stage 1, stage 2 and the divergence closed from registers) and the ones the
+    first version recomputes inside the loop must both be the reference's, bit for bit (rhs included)."""
+    Lx, Ly = 2.0, 1.0
+    u, v, p = rand_fields(nx, ny, 7 * nx + ny)
+    u[40:44, 50:70] = 0.0
+    v[40:44, 50:70] = -0.0
+    v[52, 60:64] = 1e300          # products and differences overflow
+    u[45, 70:74] = -1e300
+    u[60, 81] = 8e307             # 2 * q overflows in the Laplacian
+    u[48, 90] = np.inf
+    v[55, 100] = np.nan
+    u[ny // 2, nx - 40] = -np.inf
+    v[ny - 12, 45:47] = 1.7e308
+    bc, Re, CFL = cfdo.preset(preset, Ly)
+    sim = cfdo.Sim(port, nx, ny, Lx, Ly)
+    sim.u[:], sim.v[:], sim.p[:] = u, v, p
+    s = cfd.Solver(nx, ny, Lx, Ly)
+    s.set_march_kernel(march)
+    s.upload(u, v, p)
+    gbc = cfd.preset(preset, Ly)[0]
+    for step in range(2):  # the second step starts from the sanitised state and large, finite values
+        dt = sim.step(bc, Re, CFL, cfdo.make_params("mg"), dt_override)
+        info = s.step(gbc, Re, CFL, cfd.make_params("mg"), dt_override)
+        gu, gv, gp, grhs = s.download()
+        assert info.dt == dt, (step, info.dt, dt)
+        assert same(gu, sim.u), ("u", step, nbad(gu, sim.u), where_bad(gu, sim.u))
+        assert same(gv, sim.v), ("v", step, nbad(gv, sim.v), where_bad(gv, sim.v))
+        assert same(gp, sim.p), ("p", step, nbad(gp, sim.p), where_bad(gp, sim.p))
+        assert same(grhs[1:-1, 1:-1], sim.rhs[1:-1, 1:-1]), ("rhs", step, nbad(grhs[1:-1, 1:-1], sim.rhs[1:-1, 1:-1]))
+        if step == 0:
+            assert info.nonfinite & 1
+
+
+def test_marching_kernels_agree_bitwise_2048(cfd):
+    """k_rhs_march2 against the first version on a grid the oracle would be slow on: State and work arrays after 3 steps."""
+    nx, ny = 2048, 1536
+    u, v, p = rand_fields(nx, ny, 43)
+    u[700:704, 900:940] = 1e300
+    v[300, 1000:1004] = -np.inf
+    outs = []
+    for march in (1, 2):
+        s = cfd.Solver(nx, ny, 2.0, 1.5)
+        s.set_march_kernel(march)
+        s.upload(u, v, p)
+        bc, Re, CFL = cfd.preset("jet", 1.5)
+        for _ in range(3):
+            s.step(bc, Re, CFL, cfd.make_params("mg"))
+        outs.append(s.download() + s.download_work())
+    for a, b in zip(outs[0], outs[1]):
+        assert same(a, b), (nbad(a, b), where_bad(a, b))
+
+
 def test_kernel_variants_agree_bitwise_1024(cfd):
     """The optimised kernels (variant 1) against the simple ones (variant 0) on a grid the oracle would be slow on."""
     nx = ny = 1024
