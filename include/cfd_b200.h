@@ -141,7 +141,9 @@ int cfd_b200_smoother_strip_for(int nx, int ny, int sm_count);
 int cfd_b200_last_smoother(const cfd_b200_solver *s);
 /* Which kernels ran the last PCG solve: 1 = k_pcg_coop (the whole solve in one cooperative persistent launch; grids whose
  * p, r, s fit into the SMs' shared memory), 2 = the streaming pair k_pcg_phase1_march / _phase2_march, 3 = the tile pair
- * k_pcg_phase1 / _phase2, 0 = none yet. */
+ * k_pcg_phase1 / _phase2, 4 = k_pcg_cluster (grids of at most 512 x 256 cells: the whole solve inside one 16-CTA thread-block
+ * cluster, hardware cluster barriers, sums and halo rows through distributed shared memory; k_pcg_coop behind it as its
+ * guarded slow path), 0 = none yet. */
 int cfd_b200_last_pcg(const cfd_b200_solver *s);
 /* First owned cell row and number of owned cell rows of this handle (0, ny for a single-GPU handle). */
 int cfd_b200_slab_rows(const cfd_b200_solver *s, int *row0, int *nrows);

@@ -263,7 +263,8 @@ class Solver:
     def last_pcg(self) -> str:
         """Kernels that ran the last PCG solve."""
         return ("none", "k_pcg_coop (whole solve, one cooperative launch)", "k_pcg_phase1_march + k_pcg_phase2_march (one iteration)",
-                "k_pcg_phase1 + k_pcg_phase2 (one iteration)")[self.L.cfd_b200_last_pcg(self.h)]
+                "k_pcg_phase1 + k_pcg_phase2 (one iteration)",
+                "k_pcg_cluster (whole solve, one 16-CTA cluster)")[self.L.cfd_b200_last_pcg(self.h)]
 
     def _check(self, rc):
         if rc != 0:

@@ -18,6 +18,7 @@
 #include "kernels_step.cuh"
 #include "kernels_rhs_march.cuh"
 #include "kernels_rhs_march2.cuh"
+#include "kernels_pcg_cluster.cuh"
 #include "kernels_rbgs_fused.cuh"
 #include "kernels_rbgs_stream.cuh"
 #include "kernels_vcycle.cuh"
@@ -103,7 +104,7 @@ struct cfd_b200_solver {
     int march_kernel = -1; // marching advection kernel: 2 = k_rhs_march2 (default), 1 = first version; -1 = CFD_B200_MARCH not read yet
     int rb_strip = 0;      // > 0: force the streaming smoother with this many rows per strip (tests, tuning)
     int last_smoother = 0; // which kernel ran the last smooth(): 1 streaming, 2 tile, 3 per-colour passes
-    int last_pcg = 0;      // which kernels ran the last PCG solve: 1 cooperative persistent, 2 streaming, 3 tiles
+    int last_pcg = 0;      // which kernels ran the last PCG solve: 1 cooperative persistent, 2 streaming, 3 tiles, 4 one cluster
     int pdl = 3; // programmatic dependent launch between consecutive kernels (bit mask, see cfd_b200_create_slab; CFD_B200_PDL=0 turns it off)
     bool cfl_cached = false;   // umax/vmax of the current device State are already in d_sc (from the last step)
     cfd_b200_bc last_bc{};
@@ -135,6 +136,7 @@ struct cfd_b200_solver {
     // cooperative persistent PCG (small grids)
     double *coop_xrows = nullptr, *coop_slots = nullptr;
     int coop_ok = -1, coop_rows = 0, coop_blocks = 0, coop_smem = 0; // -1 = not probed yet
+    int cluster_ok = 0, cluster_rows = 0, cluster_smem = 0;          // k_pcg_cluster (one 16-CTA cluster) can run this grid
 };
 
 namespace {
@@ -1084,6 +1086,26 @@ bool coop_probe(cfd_b200_solver *s) {
     cudaMemsetAsync(s->coop_slots, 0, (size_t)3 * 2 * nblk * sizeof(double), s->stream);
     s->coop_rows = R, s->coop_blocks = nblk, s->coop_smem = (int)smem;
     s->coop_ok = 1;
+    // Grids of at most 512 x 256 cells: the whole solve inside ONE cluster of 16 CTAs (kernels_pcg_cluster.cuh), with the
+    // cooperative kernel behind it as its guarded slow path.  Probed like a launch: opt-in cluster size, shared memory, occupancy.
+    static const int cl_env = getenv("CFD_B200_PCG_CLUSTER") ? atoi(getenv("CFD_B200_PCG_CLUSTER")) : 1;
+    if (cl_env && g.nx <= PK_COLS && g.ny <= PK_CTAS * PK_ROWS) {
+        const int Rc = cdiv(g.ny, PK_CTAS);
+        const size_t smem_c = (size_t)(3 * Rc + 4) * (g.nx + 2) * sizeof(double);
+        if (cudaFuncSetAttribute(k_pcg_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c) == cudaSuccess &&
+            cudaFuncSetAttribute(k_pcg_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(PK_CTAS), cfg.blockDim = dim3(PK_THREADS), cfg.dynamicSmemBytes = smem_c;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = PK_CTAS, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+            cfg.attrs = at, cfg.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, k_pcg_cluster, &cfg) == cudaSuccess && ncl >= 1)
+                s->cluster_ok = 1, s->cluster_rows = Rc, s->cluster_smem = (int)smem_c;
+        }
+        cudaGetLastError(); // a refused attribute leaves the cooperative kernel in charge
+    }
     return true;
 }
 
@@ -1097,12 +1119,25 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp, bool in_step = 
     if (pp->solver == CFD_B200_SOLVER_PCG) {
         cudaMemsetAsync(s->p, 0, s->n * sizeof(double), s->stream); // pressure.cpp:133-134
         if (single && s->variant != 0 && coop_probe(s)) { // small grid: the whole solve in one persistent kernel
-            PcgCoopArgs a{g, s->rhs, s->p, s->coop_xrows, s->coop_slots, s->d_sc, pp->tol, pp->pcg_max_iters, s->coop_rows};
+            if (s->cluster_ok) {
+                PcgClusterArgs ca{g, s->rhs, s->p, s->d_sc, pp->tol, pp->pcg_max_iters, s->cluster_rows};
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(PK_CTAS), cfg.blockDim = dim3(PK_THREADS), cfg.dynamicSmemBytes = (size_t)s->cluster_smem;
+                cfg.stream = s->stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = PK_CTAS, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+                cfg.attrs = at, cfg.numAttrs = 1;
+                CU(cudaLaunchKernelEx(&cfg, k_pcg_cluster, ca));
+                s->launches++;
+            }
+            // alone, or as the guarded slow path of k_pcg_cluster (returns at once unless that kernel met a non-finite value)
+            PcgCoopArgs a{g, s->rhs, s->p, s->coop_xrows, s->coop_slots, s->d_sc, pp->tol, pp->pcg_max_iters, s->coop_rows, s->cluster_ok};
             void *args[] = {&a};
             CU(cudaLaunchCooperativeKernel((void *)k_pcg_coop, dim3(s->coop_blocks), dim3(PC_THREADS), args,
                                            (size_t)s->coop_smem, s->stream));
             s->launches++;
-            s->last_pcg = 1;
+            s->last_pcg = s->cluster_ok ? 4 : 1;
             if (!in_step) LAUNCH(s, k_solve_finish, 1, 1, s->d_sc);
             return 0;
         }

@@ -79,6 +79,7 @@ struct Scalars {
     // consumer -- 0 stand-alone wait kernel, 1 a consumer kernel's edge blocks, 2 a reduction, 3 the handshake exchange
     unsigned long long wait_ns[4], wait_n[4];
     int rb_redo;            // k_rbgs_stream met a non-finite value: the guarded tile kernel redoes this smooth()
+    int pcg_redo;           // k_pcg_cluster met a non-finite value: the guarded cooperative kernel behind it redoes the solve
 };
 
 // Programmatic dependent launch (sm_90+): every kernel of the path starts with pdl_begin().  launch_dependents lets

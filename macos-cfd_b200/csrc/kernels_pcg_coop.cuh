@@ -29,6 +29,7 @@ struct PcgCoopArgs {
     double tol;
     int max_iters;
     int rows_per_block;
+    int retry_only; // 1: run only if k_pcg_cluster (launched just before) gave up on a non-finite value (Scalars::pcg_redo)
 };
 
 // Sum of the blocks' partials, identical in every block: warp 0 loads them strided (independent loads), adds its
@@ -48,6 +49,7 @@ __device__ __forceinline__ void pc_sum(const double *slots, int nblk, int nv, do
 }
 
 __global__ void __launch_bounds__(PC_THREADS) k_pcg_coop(PcgCoopArgs A) {
+    if (A.retry_only && !A.sc->pcg_redo) return; // uniform over the grid: nobody reaches a barrier
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double sm[];
     const Geom &g = A.g;
@@ -200,5 +202,6 @@ __global__ void __launch_bounds__(PC_THREADS) k_pcg_coop(PcgCoopArgs A) {
         sc->beta = beta;
         sc->first = first ? 1 : 0;
         sc->done = 1;
+        sc->pcg_redo = 0;
     }
 }

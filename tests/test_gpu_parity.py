@@ -236,6 +236,33 @@ def test_pressure_solve_pcg(cfd, port, nx, ny, Lx, Ly, variant):
         assert same(gp[0, :], op[0, :]) and same(gp[:, 0], op[:, 0])  # ghosts are 0 after PCG
 
 
+@pytest.mark.parametrize("nx,ny", [(64, 32), (300, 211), (512, 256)])
+def test_pcg_nonfinite_rhs_takes_the_guarded_kernel(cfd, port, nx, ny):
+    """Non-finite entries in the right-hand side: the reference's guards turn them into zeros (pressure.cpp:20-60).  The
+    cluster-resident solve computes without guards, notices, gives up and the guarded cooperative kernel redoes the solve."""
+    rhs = rand_fields(nx, ny, 8)[2]
+    rhs[5, 7], rhs[9, 11], rhs[3, 3] = np.nan, np.inf, -np.inf
+    s = cfd.Solver(nx, ny, 2.0, 1.0)
+    for tol, cap in ((1e-8, 60), (1e-2, 500)):
+        s.upload(p=np.zeros_like(rhs), rhs=rhs)
+        op = np.zeros_like(rhs)
+        ores, oit = port.pressure_solve(nx, ny, 2.0, 1.0, op, rhs, cfdo.make_params("pcg", tol=tol, pcg_max_iters=cap))
+        gres, git = s.pressure_solve(cfd.make_params("pcg", tol=tol, pcg_max_iters=cap))
+        gp = s.download()[2]
+        assert "k_pcg_coop" in s.last_pcg or "k_pcg_cluster" in s.last_pcg
+        assert abs(git - oit) <= 1, (tol, cap, git, oit)
+        if git == oit:
+            assert rel_l2(gp, op) <= PCG_TOL, (tol, cap, rel_l2(gp, op))
+            assert abs(gres - ores) <= 1e-8 * max(ores, 1e-300)
+    # and a clean right-hand side afterwards goes through the cluster kernel again
+    rhs2 = rand_fields(nx, ny, 9)[2]
+    s.upload(p=np.zeros_like(rhs2), rhs=rhs2)
+    op = np.zeros_like(rhs2)
+    ores, oit = port.pressure_solve(nx, ny, 2.0, 1.0, op, rhs2, cfdo.make_params("pcg", tol=1e-8, pcg_max_iters=40))
+    gres, git = s.pressure_solve(cfd.make_params("pcg", tol=1e-8, pcg_max_iters=40))
+    assert abs(git - oit) <= 1 and rel_l2(s.download()[2], op) <= PCG_TOL
+
+
 def test_pcg_breakdown_and_zero_rhs(cfd, port):
     nx, ny = 16, 16
     s = cfd.Solver(nx, ny, 1.0, 1.0)
