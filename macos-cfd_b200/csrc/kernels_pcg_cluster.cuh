@@ -12,10 +12,12 @@
 //   * a thread owns one column of its CTA's band of <= 16 rows: its s values and Ap stay in REGISTERS for the iteration
 //     (the y-neighbours are its own registers, the x-neighbours and the halo cells come from shared memory), so Ap is
 //     computed once per iteration and there is no index arithmetic in the loops.
-// Measured (512 x 256, 200 iterations, SM cycles of CTA 0 per iteration): 12 300 in the sweeps + 5 000 in the two
-// reductions / barriers = 8.3 us against 9.2 us of the cooperative kernel.  The sweeps are latency-bound (a branch per row:
-// the rows' dependency chains do not overlap); straight-line sweeps spilt (16 rows of temporaries next to 64 registers of
-// state: 20 800 cycles) and 1024 threads x 8 rows paid more at the barriers than they gained (22 600) -- both dropped.
+// Measured (512 x 256, 200 iterations): 6.0 us per iteration against 9.2 us of the cooperative kernel (step 1.92 -> 1.27 ms).
+// The sweeps are bound by the latency of dependent fp64 operations, so how many rows of a column the compiler may interleave
+// decides: a branch per row (chains one after the other) 8.3 us -- 12 300 of 17 300 SM cycles in the sweeps --, groups of
+// 2 / 4 / 8 rows behind one test 7.4 / 6.8 / 6.7 us, the whole column behind one test 6.0 us (PK_SWEEP; threads right of the
+// grid skip the sweep: masking their stores instead made the compiler spill, 14.0 us).  1024 threads x 8 rows paid more at
+// the barriers than they gained (10.9 us).  What is left: ~2.5 us per iteration in the two reductions + cluster barriers.
 // The isfinite guards of the reference (pressure.cpp:20-44 on every operand of the Laplacian, :49-60 on every operand of a
 // dot product) are identities while every value is finite.  This kernel computes without them and folds the high words of
 // Ap, z = inv_diag * r and p into running maxima; the flag rides on every reduction, so all CTAs learn of a non-finite
@@ -34,6 +36,21 @@
 #define PK_COLS 512
 #define PK_CTAS 16     // non-portable cluster size (opt-in by attribute; probed before use)
 #define PK_ROWS 16     // rows per CTA: ny <= 256
+
+#ifndef PK_GROUP
+#define PK_GROUP 16 // rows of a column whose dependency chains may overlap (one basic block per group)
+#endif
+// One sweep over this thread's column: the body (the macro's last argument) for every row lj (a compile-time constant inside the body) that the CTA owns.  Rows
+// are taken in groups of PK_GROUP behind ONE test, so that the compiler can interleave their chains; a branch per row ran
+// them one after the other, all 16 rows in one block spilt.
+#define PK_SWEEP(lj, ...)                                                                       \
+    _Pragma("unroll") for (int g0_ = 0; g0_ < PK_ROWS; g0_ += PK_GROUP) {                       \
+        if (g0_ + PK_GROUP <= nrows && col) {                                                   \
+            _Pragma("unroll") for (int k_ = 0; k_ < PK_GROUP; ++k_) { const int lj = g0_ + k_; __VA_ARGS__ } \
+        } else {                                                                                \
+            _Pragma("unroll") for (int k_ = 0; k_ < PK_GROUP; ++k_) { const int lj = g0_ + k_; if (lj < nrows && col) __VA_ARGS__ } \
+        }                                                                                       \
+    }
 
 struct PcgClusterArgs {
     Geom g;
@@ -145,13 +162,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_pcg_cluster(PcgClusterArgs A)
 
     while (!done && !redo) {
         // ---- A: direction update of my column (+ the two halo cells from the neighbours' r rows), Ap, dot(s, Ap)
-#pragma unroll
-        for (int lj = 0; lj < PK_ROWS; ++lj)
-            if (lj < nrows && col) {
-                const double z = inv_diag * r[lj * S + ii];
-                sreg[lj] = first ? z : z + beta * sreg[lj];
-                s[(lj + 1) * S + ii] = sreg[lj];
-            }
+        PK_SWEEP(lj, {
+            const double z = inv_diag * r[lj * S + ii];
+            sreg[lj] = first ? z : z + beta * sreg[lj];
+            s[(lj + 1) * S + ii] = sreg[lj];
+        })
         if (col) { // the neighbours' direction in the halo cells, recomputed from their r rows (the same bits as they hold)
             double v = 0.0;
             if (live_lo) {
@@ -168,17 +183,15 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_pcg_cluster(PcgClusterArgs A)
         }
         __syncthreads();
         double d = 0.0;
-#pragma unroll
-        for (int lj = 0; lj < PK_ROWS; ++lj)
-            if (lj < nrows && col) {
-                const double c = sreg[lj], l = s[(lj + 1) * S + ii - 1], rt = s[(lj + 1) * S + ii + 1];
-                const double bl = lj > 0 ? sreg[lj > 0 ? lj - 1 : 0] : shb;
-                const double ab = lj + 1 < nrows ? sreg[lj + 1 < PK_ROWS ? lj + 1 : lj] : sha;
-                const double Ap = (rt - 2.0 * c + l) * idx2 + (ab - 2.0 * c + bl) * idy2;
-                apreg[lj] = Ap;
-                d += c * Ap;
-                track(Ap);
-            }
+        PK_SWEEP(lj, {
+            const double c = sreg[lj], l = s[(lj + 1) * S + ii - 1], rt = s[(lj + 1) * S + ii + 1];
+            const double bl = lj > 0 ? sreg[lj > 0 ? lj - 1 : 0] : shb;
+            const double ab = lj + 1 < nrows ? sreg[lj + 1 < PK_ROWS ? lj + 1 : lj] : sha;
+            const double Ap = (rt - 2.0 * c + l) * idx2 + (ab - 2.0 * c + bl) * idy2;
+            apreg[lj] = Ap;
+            d += c * Ap;
+            track(Ap);
+        })
         cluster_partial(slotA, d, bad(), 0.0, 2);
         cluster.sync();
         if (cluster_total(slotA, 1) > 0.0) { redo = true; break; }
@@ -190,22 +203,20 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_pcg_cluster(PcgClusterArgs A)
         const double alpha = rho / denom;
         // ---- B: p += alpha s, r -= alpha Ap, pin, dot(r,r), dot(r,z); my boundary r rows go to the neighbours
         double rr = 0.0, rz = 0.0;
-#pragma unroll
-        for (int lj = 0; lj < PK_ROWS; ++lj)
-            if (lj < nrows && col) {
-                double pv = p[lj * S + ii] + alpha * sreg[lj];
-                const double rv = r[lj * S + ii] - alpha * apreg[lj];
-                if (g.j0 == 0 && j0 + lj == 1 && ii == 1) pv = 0.0; // re-pin p(0,0), pressure.cpp:200
-                p[lj * S + ii] = pv;
-                r[lj * S + ii] = rv;
-                const double z = inv_diag * rv;
-                rr += rv * rv;
-                rz += rv * z;
-                track(z);
-                track(pv);
-                if (lj == 0) rfirst = rv;
-                if (lj == nrows - 1) rlast = rv;
-            }
+        PK_SWEEP(lj, {
+            double pv = p[lj * S + ii] + alpha * sreg[lj];
+            const double rv = r[lj * S + ii] - alpha * apreg[lj];
+            if (g.j0 == 0 && j0 + lj == 1 && ii == 1) pv = 0.0; // re-pin p(0,0), pressure.cpp:200
+            p[lj * S + ii] = pv;
+            r[lj * S + ii] = rv;
+            const double z = inv_diag * rv;
+            rr += rv * rv;
+            rz += rv * z;
+            track(z);
+            track(pv);
+            if (lj == 0) rfirst = rv;
+            if (lj == nrows - 1) rlast = rv;
+        })
         send_rows(rfirst, rlast);
         cluster_partial(slotB, rr, rz, bad(), 3);
         cluster.sync();
