@@ -1128,8 +1128,12 @@ int enqueue_solve(cfd_b200_solver *s, const cfd_b200_params *pp, bool in_step = 
                 at[0].id = cudaLaunchAttributeClusterDimension;
                 at[0].val.clusterDim.x = PK_CTAS, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
                 cfg.attrs = at, cfg.numAttrs = 1;
-                CU(cudaLaunchKernelEx(&cfg, k_pcg_cluster, ca));
-                s->launches++;
+                if (cudaLaunchKernelEx(&cfg, k_pcg_cluster, ca) == cudaSuccess) {
+                    s->launches++;
+                } else { // a cluster of this size cannot be placed after all: the cooperative kernel alone, from now on
+                    cudaGetLastError();
+                    s->cluster_ok = 0;
+                }
             }
             // alone, or as the guarded slow path of k_pcg_cluster (returns at once unless that kernel met a non-finite value)
             PcgCoopArgs a{g, s->rhs, s->p, s->coop_xrows, s->coop_slots, s->d_sc, pp->tol, pp->pcg_max_iters, s->coop_rows, s->cluster_ok};

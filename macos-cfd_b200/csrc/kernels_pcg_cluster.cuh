@@ -28,8 +28,6 @@
 #pragma once
 #include <cooperative_groups.h>
 
-#include <type_traits>
-
 #include "kernels_pcg_coop.cuh"
 
 #define PK_THREADS 512 // one column per thread: nx <= 512
